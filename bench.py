@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the FFT acquisition search (BASELINE.json metric: correlation cells/s).
+
+Workload (BASELINE.json configs[1]): GPS L1 C/A, all 32 PRNs, 10 ms coherent, +-10 kHz /
+250 Hz (80 Doppler bins), 16.368 Msps complex IQ => N = 163680 lags, R = 32, D = 80, B = 1,
+variant-A search (metric q[idx]/mean q, argmax over the first code period).
+A step = one pass of the hot path over one capture: replica spectra + wipe-off + forward
+FFTs + fused correlate + finalize (replica FFT set-up included).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): the Doppler grid is sharded — rank k owns 80 bins of an
+N-times wider grid (weak scaling) — and one NCCL all-gather of the per-PRN records precedes
+the final strict-'>' reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'gnss-dsp-tools_b200')]
+
+FS = 16368000.0
+N = 163680
+R = 32
+D_PER_GPU = 80
+DOPPLER_STEP = 250.0
+N_LAGS = 16368
+CODE_L = 1023
+WORKLOAD = 'gps-l1-ca 32 PRN x 80 Doppler x 163680 lags, 10 ms coherent @16.368 Msps (BASELINE configs[1])'
+
+
+def make_inputs(seed=2):
+    """Synthetic capture (8 planted satellites) and the 32 time-domain replicas."""
+    from gnsstools import acquire, synth
+    sig = acquire.Signal('gps.ca', FS, N, lambda ms: ms // 10, normalize=True, mod_L=True, periods=10)
+    rng = np.random.default_rng(seed)
+    sats = [(int(p), float(rng.integers(-38, 38)) * 250.0, float(rng.uniform(0, 1023)), 1.0)
+            for p in rng.choice(np.arange(1, 33), 8, replace=False)]
+    x = synth.capture(sig, ms=10, sats=sats, seed=seed, extra_ms=0)
+    rep = np.stack([acquire.replica(sig, p) for p in range(1, 33)])
+    return sig, x, rep, sats
+
+
+def doppler_freqs(world):
+    """Global grid: world*80 bins of 250 Hz centred on 0; returns normalised NCO freqs."""
+    D = D_PER_GPU * world
+    bins = np.arange(-DOPPLER_STEP * D / 2, DOPPLER_STEP * D / 2, DOPPLER_STEP)
+    return bins, -bins / FS
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except Exception:
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7), ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_baseline(x, rep_chips_prns, bins, cores=None, n_prn=None, n_bins=None):
+    """The oracle (numpy/scipy restatement of the reference search()) on the host cores,
+    fanned out over PRNs with multiprocessing like acquire-gps-l1.py:105-108.
+    Bounded sample of the same workload: n_prn PRNs x n_bins Doppler bins x N lags."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    n_prn = n_prn or min(R, cores)
+    n_bins = n_bins or 16
+    grid = (float(bins[0]), float(bins[0]) + n_bins * DOPPLER_STEP, DOPPLER_STEP)
+    tasks = [(x, p, grid) for p in rep_chips_prns[:n_prn]]
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context('fork').Pool(min(cores, n_prn)) as pool:
+            pool.map(_cpu_task, tasks)
+    else:
+        list(map(_cpu_task, tasks))
+    dt = time.perf_counter() - t0
+    cells = n_prn * n_bins * N
+    return cells / dt, dt, dict(cores=min(cores, n_prn) if cores > 1 else 1,
+                                sample='%d PRN x %d Doppler bins x %d lags of the same capture, %.1f s wall' % (n_prn, n_bins, N, dt))
+
+
+def _cpu_task(t):
+    from oracle import acq_oracle as orc
+    import gnsstools.gps.ca as ca
+    x, prn, grid = t
+    return orc.search(x, ca.ca_code(prn), FS, N, grid, 1, normalize=True, mod_L=True, lag_limit=N_LAGS, periods=10)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: the reference is pure Python
+    and cannot travel to the GPU box) on all host cores, same metric/config."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sig, x, rep, sats = make_inputs()
+    bins, _ = doppler_freqs(1)
+    x128 = x.astype(np.complex128)
+    prns = list(range(1, 33))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, info = cpu_baseline(x128, prns, bins)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    line = {
+        'impl': 'reference', 'metric': 'correlation cells/s (PRNxDopplerxcode-phase)', 'value': value, 'unit': 'cells/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': info['sample']},
+        'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': info['cores'], 'kind': 'port', 'sample': info['sample']},
+        'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def merge_records(all_rec, d_per_rank):
+    """Rank-ordered strict-'>' merge of per-rank per-PRN records -> global (metric, lag, dbin).
+    Ranks hold ascending contiguous Doppler ranges, so ties go to the lowest Doppler bin
+    exactly as the single-GPU scan (acquire-gps-l1.py:36)."""
+    world = all_rec.shape[0]
+    best = all_rec[0].copy()
+    for k in range(1, world):
+        rec = all_rec[k]
+        take = (rec['dbin'] >= 0) & (rec['metric'] > best['metric'])
+        shifted = rec.copy()
+        shifted['dbin'] = np.where(rec['dbin'] >= 0, rec['dbin'] + k * d_per_rank, -1)
+        best = np.where(take, shifted, best)
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gnsstools import _native
+
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    sig, x, rep, sats = make_inputs()
+    bins, freqs = doppler_freqs(world)
+    my = slice(rank * D_PER_GPU, (rank + 1) * D_PER_GPU)
+    my_f = np.ascontiguousarray(freqs[my])
+
+    eng = _native.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_profiling(True)
+
+    # ---- device-resident inputs for `value`
+    x_dev = torch.from_numpy(x.view(np.float32).copy()).to(dev)
+    rep_dev = torch.from_numpy(rep).to(dev)
+    rec_dev = torch.zeros(R * 4, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(world * R * 4, dtype=torch.int32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    # ---- pinned host inputs for `e2e`
+    x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
+    rep_pin = torch.from_numpy(rep).pin_memory()
+    rec_pin = torch.zeros(R * 4, dtype=torch.int32).pin_memory()
+    x_dev2 = torch.empty_like(x_dev)
+    rep_dev2 = torch.empty_like(rep_dev)
+
+    def step_resident():
+        eng.set_signal_device(x_dev.data_ptr(), x.size)
+        eng.set_replicas_device(rep_dev.data_ptr(), R, N)
+        eng.search_device(my_f, N, 1, True, N_LAGS, rec_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec_dev)
+
+    def step_e2e():
+        x_dev2.copy_(x_pin, non_blocking=True)
+        rep_dev2.copy_(rep_pin, non_blocking=True)
+        eng.set_signal_device(x_dev2.data_ptr(), x.size)
+        eng.set_replicas_device(rep_dev2.data_ptr(), R, N)
+        eng.search_device(my_f, N, 1, True, N_LAGS, rec_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec_dev)
+            rec_pin_all.copy_(gathered, non_blocking=True)
+        else:
+            rec_pin.copy_(rec_dev, non_blocking=True)
+        stream.synchronize()
+
+    rec_pin_all = torch.zeros(world * R * 4, dtype=torch.int32).pin_memory() if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, K, W):
+        for _ in range(W):
+            step()
+        barrier()
+        eng.stage_times(reset=True)
+        l0 = eng.launch_count()
+        evs = []
+        for _ in range(K):
+            flush.zero_()                          # evict L2 between timed iterations (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step()
+            b.record(stream)
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.launch_count() - l0, eng.stage_times(reset=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K, W = args.steps, args.warmup
+    ms_total, launches, stages = timed(step_resident, K, W)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, K, W)
+
+    # ---- correctness of what was just timed: planted satellites recovered
+    rec = rec_pin_all.numpy().view(_native.RECORD_DTYPE).reshape(world, R) if world > 1 else \
+        rec_pin.numpy().view(_native.RECORD_DTYPE).reshape(1, R)
+    best = merge_records(rec, D_PER_GPU)
+    found = 0
+    for prn, fd, phase, _ in sats:
+        b = best[prn - 1]
+        if b['dbin'] >= 0 and bins[b['dbin']] == fd and abs((10.0 * CODE_L * b['lag'] / N) % CODE_L - phase) < 0.2:
+            found += 1
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cells = R * D_PER_GPU * world * N            # whole job, all ranks
+    value = cells / (ms_total / K * 1e-3)
+    e2e_value = cells / (ms_e2e / K * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    # dominant kernel(s): the correlate stage (rows + columns kernels of the large plan).
+    corr_ms = stages['corr'][0] + stages['corr_rows'][0]
+    corr_launches = stages['corr'][1] + stages['corr_rows'][1]
+    alg_bytes_per_step = 16.0 * R * D_PER_GPU * 1 * N          # 16 B per cell-block, this rank
+    achieved = alg_bytes_per_step * K / (corr_ms * 1e-3) / 1e9 if corr_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('corr_dram_bytes_per_step')
+        except Exception:
+            traffic = None
+    line = {
+        'metric': 'correlation cells/s (PRNxDopplerxcode-phase)', 'value': value, 'unit': 'cells/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'R': R, 'D_per_gpu': D_PER_GPU, 'N': N, 'B': 1,
+                   'sharding': 'doppler bins, %d per GPU, one all-gather of per-PRN records' % D_PER_GPU,
+                   'l2': 'flushed between timed steps (256 MiB memset, untimed)', 'plan': eng.plan_info(),
+                   'planted_found': '%d/%d' % (found, len(sats))},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'cells/s', 'ms_per_step': ms_e2e / K,
+                'h2d_bytes_per_step': int(x.nbytes + rep.nbytes + my_f.nbytes), 'd2h_bytes_per_step': int(R * 16 * world)},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
+                     'kernel': 'correlate stage = k_corr_rows + k_corr_cols (one logical fused correlate, two launches per chunk)',
+                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
+                     'kernel_ms_per_step': corr_ms / K, 'kernel_launches_per_step': corr_launches / K,
+                     'stage_ms_per_step': {k: v[0] / K for k, v in stages.items()}},
+    }
+    if not args.no_cpu_baseline:
+        v, dt, info = cpu_baseline(x.astype(np.complex128), list(range(1, 33)), bins[:D_PER_GPU])
+        line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': info['cores'], 'kind': 'port', 'sample': info['sample']}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

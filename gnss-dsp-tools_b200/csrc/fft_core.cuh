@@ -1,0 +1,275 @@
+// Mixed-radix complex FFT building blocks that run on a shared-memory tile.
+//
+// Data model. A *tile* holds `ncols` independent transforms of length F laid out
+// batch-fastest: element e of column c lives at tile[e*WP + c]. Butterflies are
+// assigned to threads as (column fastest, butterfly next), so a half-warp always touches
+// 16 consecutive float2 — bank-conflict-free for every radix and stride, which is what
+// lets one routine serve the non-power-of-two lengths GNSS sample rates produce
+// (30690 = 2*3^2*5*11*31, 163680 = 2^5*3*5*11*31, 81920 = 2^14*5, ...).
+//
+// Transform pair. Forward is decimation-in-frequency, in place, natural order in ->
+// mixed-radix digit-reversed ("position") order out. Inverse is the exact adjoint
+// (stages reversed, conjugate twiddles first, conjugate butterflies), position order in
+// -> natural order out, unnormalised. The acquisition path multiplies spectra element by
+// element, so the frequency domain never needs natural order and no reordering pass exists.
+#pragma once
+#include "cuda_compat.h"
+#include <type_traits>
+
+namespace acq {
+
+constexpr int kMaxStages = 10;
+
+// One in-shared-memory transform length and its radix schedule (host-built, see fft_plan.h).
+struct SubPlan {
+  int F;                    // transform length
+  int ns;                   // number of stages
+  int radix[kMaxStages];    // radix of stage j (forward order)
+  int m[kMaxStages];        // element stride of stage j = product of the later radices
+  const float2* tw;         // device table: tw[k] = exp(-2*pi*i*k/F), k < F
+};
+
+// ---------------------------------------------------------------- complex helpers
+__host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+// a * (-i)
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// ---------------------------------------------------------------- compile-time trig
+__host__ __device__ constexpr double cx_sin(double x) {
+  double term = x, sum = x;
+  for (int k = 1; k < 24; ++k) { term *= -x * x / ((2.0 * k) * (2.0 * k + 1.0)); sum += term; }
+  return sum;
+}
+__host__ __device__ constexpr double cx_cos(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 24; ++k) { term *= -x * x / ((2.0 * k - 1.0) * (2.0 * k)); sum += term; }
+  return sum;
+}
+__host__ __device__ constexpr double cx_angle(int k, int n) {
+  // 2*pi*k/n reduced to (-pi, pi]
+  k %= n;
+  double t = 6.283185307179586476925286766559 * (double)k / (double)n;
+  return t > 3.14159265358979323846 ? t - 6.283185307179586476925286766559 : t;
+}
+template <int P> struct TrigTab { float c[P]; float s[P]; };
+template <int P> __host__ __device__ constexpr TrigTab<P> make_trig_tab() {
+  TrigTab<P> t{};
+  for (int k = 0; k < P; ++k) { t.c[k] = (float)cx_cos(cx_angle(k, P)); t.s[k] = (float)cx_sin(cx_angle(k, P)); }
+  return t;
+}
+
+template <int P> constexpr TrigTab<P> kTrig = make_trig_tab<P>();
+
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// ---------------------------------------------------------------- forward butterflies
+// dft<R>(v): v[q] <- sum_p v[p] * exp(-2*pi*i*p*q/R), in place, natural order.
+template <int R> struct Dft;
+
+template <> struct Dft<2> {
+  static __device__ __forceinline__ void run(float2* v) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  }
+};
+template <> struct Dft<4> {
+  static __device__ __forceinline__ void run(float2* v) {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), t3 = cmul_mi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2); v[2] = csub(t0, t2);
+    v[1] = cadd(t1, t3); v[3] = csub(t1, t3);
+  }
+};
+template <> struct Dft<8> {
+  static __device__ __forceinline__ void run(float2* v) {
+    const float h = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4>::run(e); Dft<4>::run(o);
+    // o[k] *= W8^k
+    o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+    o[2] = cmul_mi(o[2]);
+    o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = cadd(e[k], o[k]); v[k + 4] = csub(e[k], o[k]); }
+  }
+};
+template <> struct Dft<16> {
+  static __device__ __forceinline__ void run(float2* v) {
+    const float h = 0.70710678118654752440f;
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    float2 e[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    Dft<8>::run(e); Dft<8>::run(o);
+    // o[k] *= W16^k = (cos(k*pi/8), -sin(k*pi/8))
+    o[1] = cmul(o[1], make_float2(c1, -s1));
+    o[2] = make_float2(h * (o[2].x + o[2].y), h * (o[2].y - o[2].x));
+    o[3] = cmul(o[3], make_float2(s1, -c1));
+    o[4] = cmul_mi(o[4]);
+    o[5] = cmul(o[5], make_float2(-s1, -c1));
+    o[6] = make_float2(h * (o[6].y - o[6].x), -h * (o[6].x + o[6].y));
+    o[7] = cmul(o[7], make_float2(-c1, -s1));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = cadd(e[k], o[k]); v[k + 8] = csub(e[k], o[k]); }
+  }
+};
+
+// Odd prime radix: split into symmetric / antisymmetric halves so every output pair
+// (k, P-k) shares its real-coefficient sums: (P-1)^2 real FMAs instead of 4*P^2.
+template <int P> struct Dft {
+  static_assert(P % 2 == 1 && P >= 3, "generic butterfly is for odd radices");
+  static __device__ __forceinline__ void run(float2* v) {
+    constexpr int H = (P - 1) / 2;
+    float2 a[H + 1], b[H + 1];
+    const float2 x0 = v[0];
+    float2 s0 = x0;
+    static_for<1, H + 1>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      a[j] = cadd(v[j], v[P - j]);
+      b[j] = csub(v[j], v[P - j]);
+      s0 = cadd(s0, a[j]);
+    });
+    v[0] = s0;
+    static_for<1, H + 1>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      float2 re = x0, im = make_float2(0.f, 0.f);
+      static_for<1, H + 1>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr float c = kTrig<P>.c[(j * k) % P];
+        constexpr float s = kTrig<P>.s[(j * k) % P];
+        re.x += c * a[j].x; re.y += c * a[j].y;
+        im.x += s * b[j].x; im.y += s * b[j].y;
+      });
+      v[k] = make_float2(re.x + im.y, re.y - im.x);        // re - i*im
+      v[P - k] = make_float2(re.x - im.y, re.y + im.x);    // re + i*im
+    });
+  }
+};
+
+// ---------------------------------------------------------------- one stage over a tile
+// Threads are viewed as (tc = tid % TW, tb = tid / TW): tc walks columns, tb walks butterflies.
+constexpr int kTW = 16;
+
+template <int R, bool INV>
+__device__ __forceinline__ void stage_tile(float2* tile, int WP, int ncols, int F, int m,
+                                           const float2* __restrict__ tw) {
+  const int tc = threadIdx.x & (kTW - 1);
+  const int tb = threadIdx.x / kTW;
+  const int nb = blockDim.x / kTW;
+  const int nbf = F / R;
+  const int twstep = F / (R * m);
+  const int estride = m * WP;
+  for (int bf = tb; bf < nbf; bf += nb) {
+    const int blk = bf / m;
+    const int i = bf - blk * m;
+    float2* base = tile + (blk * R * m + i) * WP;
+    constexpr bool kCacheTw = R <= 8;      // larger radices reload (broadcast, L1-resident)
+    float2 w[kCacheTw ? R : 1];
+    const float2* twp = tw + 0;
+    const int twi = i * twstep;
+    if (kCacheTw && m > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) w[q] = __ldg(&twp[q * twi]);
+    }
+    for (int c = tc; c < ncols; c += kTW) {
+      float2* p = base + c;
+      float2 v[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[q] = p[q * estride];
+      if (INV) {
+        if (m > 1) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], kCacheTw ? w[q] : __ldg(&twp[q * twi]));
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
+        Dft<R>::run(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
+      } else {
+        Dft<R>::run(v);
+        if (m > 1) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[q] = cmul(v[q], kCacheTw ? w[q] : __ldg(&twp[q * twi]));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) p[q * estride] = v[q];
+    }
+  }
+}
+
+// Radix classes: kernels are instantiated per class so that power-of-two plans are not
+// register-allocated for the 31-point butterfly. 0: {2,4,8,16}; 1: + {3,5}; 2: + {7,11,13,31}.
+constexpr int kNumRadixClasses = 3;
+__host__ __device__ constexpr int radix_class_of(int R) {
+  return (R == 2 || R == 4 || R == 8 || R == 16) ? 0 : ((R == 3 || R == 5) ? 1 : 2);
+}
+__host__ __device__ constexpr bool radix_supported(int R) {
+  return R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 11 || R == 13 || R == 16 || R == 31;
+}
+
+template <int RC, bool INV>
+__device__ __forceinline__ void stage_dispatch(int R, float2* tile, int WP, int ncols, int F, int m,
+                                               const float2* __restrict__ tw) {
+  switch (R) {
+    case 2: stage_tile<2, INV>(tile, WP, ncols, F, m, tw); break;
+    case 4: stage_tile<4, INV>(tile, WP, ncols, F, m, tw); break;
+    case 8: stage_tile<8, INV>(tile, WP, ncols, F, m, tw); break;
+    case 16: stage_tile<16, INV>(tile, WP, ncols, F, m, tw); break;
+    default:
+      if constexpr (RC >= 1) {
+        switch (R) {
+          case 3: stage_tile<3, INV>(tile, WP, ncols, F, m, tw); break;
+          case 5: stage_tile<5, INV>(tile, WP, ncols, F, m, tw); break;
+          default:
+            if constexpr (RC >= 2) {
+              switch (R) {
+                case 7: stage_tile<7, INV>(tile, WP, ncols, F, m, tw); break;
+                case 11: stage_tile<11, INV>(tile, WP, ncols, F, m, tw); break;
+                case 13: stage_tile<13, INV>(tile, WP, ncols, F, m, tw); break;
+                case 31: stage_tile<31, INV>(tile, WP, ncols, F, m, tw); break;
+                default: break;   // the host planner never emits other radices
+              }
+            }
+            break;
+        }
+      }
+      break;
+  }
+}
+
+// Transform every column of the tile. The caller must have synchronised after filling the
+// tile; on return all threads have passed a barrier after the last stage.
+template <int RC, bool INV>
+__device__ __forceinline__ void subfft_tile(float2* tile, int WP, int ncols, const SubPlan& sp) {
+  if (!INV) {
+    for (int j = 0; j < sp.ns; ++j) {
+      stage_dispatch<RC, false>(sp.radix[j], tile, WP, ncols, sp.F, sp.m[j], sp.tw);
+      __syncthreads();
+    }
+  } else {
+    for (int j = sp.ns - 1; j >= 0; --j) {
+      stage_dispatch<RC, true>(sp.radix[j], tile, WP, ncols, sp.F, sp.m[j], sp.tw);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace acq

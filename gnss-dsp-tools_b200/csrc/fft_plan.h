@@ -1,0 +1,121 @@
+// Host-side FFT planning: factor the transform length, choose the two-level split
+// N = N1 * N2, and build the twiddle tables (computed in double, stored as float2).
+#pragma once
+#include "fft_core.cuh"
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace acq {
+
+constexpr int kMaxSub = 1024;        // longest transform done inside one shared-memory tile
+constexpr int kMaxPrime = 31;        // largest radix the kernels instantiate
+constexpr int kMidMax = 8192;        // N <= kMidMax: whole transform resident in one CTA
+
+struct HostSubPlan {
+  int F = 0;
+  std::vector<int> radix, m;
+  std::vector<int> pos_of_freq;      // position of frequency k after the forward transform
+  std::vector<int> freq_of_pos;
+};
+
+struct HostPlan {
+  int N = 0, N1 = 0, N2 = 0;
+  bool large = false;                // two kernels through an L2-resident scratch
+  int rclass = 0;                    // radix class of the kernels to launch (fft_core.cuh)
+  HostSubPlan s1, s2;                // s1: length N1 over stride-N2 columns; s2: length N2 over rows
+  std::vector<float2> tw1, tw2;      // exp(-2 pi i k / F)
+  std::vector<float2> twm;           // twm[p1*N2 + n2] = exp(-2 pi i k1(p1) n2 / N)
+};
+
+inline std::vector<int> prime_factors(int n) {
+  std::vector<int> f;
+  for (int p = 2; (long long)p * p <= n; ++p)
+    while (n % p == 0) { f.push_back(p); n /= p; }
+  if (n > 1) f.push_back(n);
+  return f;
+}
+
+// Radix schedule for one tile transform: powers of two grouped into 16/8/4/2, odd primes
+// as themselves; large odd radices first so the cheap power-of-two stages run at unit stride.
+inline bool make_subplan(int F, HostSubPlan& sp) {
+  sp = HostSubPlan();
+  sp.F = F;
+  if (F < 1) return false;
+  int twos = 0;
+  std::vector<int> odd;
+  for (int p : prime_factors(F)) {
+    if (p == 2) ++twos;
+    else if (!radix_supported(p)) return false;
+    else odd.push_back(p);
+  }
+  for (auto it = odd.rbegin(); it != odd.rend(); ++it) sp.radix.push_back(*it);
+  while (twos > 0) {
+    int take = (twos == 5 || twos == 6 || twos == 9) ? 3 : (twos >= 4 ? 4 : twos);
+    sp.radix.push_back(1 << take);
+    twos -= take;
+  }
+  if (sp.radix.empty()) sp.radix.push_back(1);   // F == 1: no stage
+  if (F == 1) sp.radix.clear();
+  if ((int)sp.radix.size() > kMaxStages) return false;
+  sp.m.resize(sp.radix.size());
+  int m = F;
+  for (size_t j = 0; j < sp.radix.size(); ++j) { m /= sp.radix[j]; sp.m[j] = m; }
+  // frequency k = q0 + r0*(q1 + r1*(q2 + ...)) lands at position sum_j q_j * m_j
+  sp.pos_of_freq.assign(F, 0);
+  sp.freq_of_pos.assign(F, 0);
+  for (int k = 0; k < F; ++k) {
+    int rem = k, pos = 0;
+    for (size_t j = 0; j < sp.radix.size(); ++j) { pos += (rem % sp.radix[j]) * sp.m[j]; rem /= sp.radix[j]; }
+    sp.pos_of_freq[k] = pos;
+    sp.freq_of_pos[pos] = k;
+  }
+  return true;
+}
+
+inline std::vector<float2> unit_roots(int F) {
+  std::vector<float2> t(F);
+  for (int k = 0; k < F; ++k) {
+    double a = -2.0 * M_PI * (double)k / (double)F;
+    t[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  return t;
+}
+
+// Choose N = N1*N2 with both factors tile-sized and as square as possible.
+inline bool make_plan(int N, HostPlan& pl, std::string& err) {
+  pl = HostPlan();
+  pl.N = N;
+  if (N < 4) { err = "FFT length must be >= 4"; return false; }
+  for (int p : prime_factors(N))
+    if (!radix_supported(p)) {
+      err = "FFT length " + std::to_string(N) + " has the unsupported prime factor " + std::to_string(p) +
+            " (supported: 2, 3, 5, 7, 11, 13, 31)";
+      return false;
+    }
+  int best = 0;
+  for (int a = 1; (long long)a * a <= N; ++a)
+    if (N % a == 0 && N / a <= kMaxSub) { best = a; }
+  if (best == 0) { err = "FFT length " + std::to_string(N) + " cannot be split into two factors <= 1024"; return false; }
+  // rows (contiguous, length N2) get the larger factor: longer coalesced runs.
+  pl.N1 = best; pl.N2 = N / best;
+  if (pl.N1 < 2) { err = "FFT length " + std::to_string(N) + " is prime; unsupported"; return false; }
+  pl.large = N > kMidMax;
+  if (!make_subplan(pl.N1, pl.s1) || !make_subplan(pl.N2, pl.s2)) { err = "unsupported factorisation"; return false; }
+  for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
+  for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
+  pl.tw1 = unit_roots(pl.N1);
+  pl.tw2 = unit_roots(pl.N2);
+  pl.twm.resize((size_t)N);
+  for (int p1 = 0; p1 < pl.N1; ++p1) {
+    const long long k1 = pl.s1.freq_of_pos[p1];
+    for (int n2 = 0; n2 < pl.N2; ++n2) {
+      long long e = (k1 * n2) % N;
+      double a = -2.0 * M_PI * (double)e / (double)N;
+      pl.twm[(size_t)p1 * pl.N2 + n2] = make_float2((float)cos(a), (float)sin(a));
+    }
+  }
+  return true;
+}
+
+}  // namespace acq

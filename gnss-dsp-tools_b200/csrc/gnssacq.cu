@@ -1,0 +1,484 @@
+// libgnssacq.so — C ABI (include/gnssacq.h) over the sm_100a acquisition kernels.
+#include "../../include/gnssacq.h"
+#include "fft_plan.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+using namespace acq;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(GNSSACQ_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// Working-set budgets: keep the per-chunk capture spectra and the inverse-FFT scratch
+// L2-resident (B200 L2 is ~126 MB) so the correlate kernels re-read them from L2, not HBM.
+constexpr size_t kXChunkBytes = 48u << 20;
+constexpr size_t kScratchBytes = 40u << 20;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return fail(GNSSACQ_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct gnssacq {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int64_t launches = 0;
+  size_t smem_optin = 0;
+
+  std::vector<double> nco_c128;       // 1024 x (re, im)
+  DevBuf d_nco_f32, d_nco_f64;
+
+  DevBuf d_x_own;                     // capture (owned copy)
+  const float2* d_x = nullptr;
+  int64_t n_x = 0;
+
+  HostPlan hp;
+  DevPlan dp{};
+  DevBuf d_tw1, d_tw2, d_twm;
+  DevBuf d_C;                         // replica spectra [R][N]
+  int R = 0, N = 0;
+
+  DevBuf d_X, d_scratch, d_parts, d_freq, d_rec, d_q, d_tmp;
+
+  // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
+  // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_launches[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int upload_nco(gnssacq* h) {
+  std::vector<float2> f32(kNcoSize);
+  for (int k = 0; k < kNcoSize; ++k)
+    f32[k] = make_float2((float)h->nco_c128[2 * k], (float)h->nco_c128[2 * k + 1]);
+  if (int rc = h->d_nco_f32.ensure(kNcoSize * sizeof(float2))) return rc;
+  if (int rc = h->d_nco_f64.ensure(kNcoSize * sizeof(double2))) return rc;
+  CU(cudaMemcpyAsync(h->d_nco_f32.p, f32.data(), kNcoSize * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_nco_f64.p, h->nco_c128.data(), kNcoSize * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
+  sp.F = hs.F;
+  sp.ns = (int)hs.radix.size();
+  for (int j = 0; j < kMaxStages; ++j) { sp.radix[j] = j < sp.ns ? hs.radix[j] : 1; sp.m[j] = j < sp.ns ? hs.m[j] : 1; }
+  sp.tw = tw;
+}
+
+int upload_plan(gnssacq* h, int N) {
+  if (h->hp.N == N) return 0;
+  HostPlan hp;
+  std::string err;
+  if (!make_plan(N, hp, err)) return fail(GNSSACQ_EINVAL, err);
+  if (int rc = h->d_tw1.ensure(hp.tw1.size() * sizeof(float2))) return rc;
+  if (int rc = h->d_tw2.ensure(hp.tw2.size() * sizeof(float2))) return rc;
+  if (int rc = h->d_twm.ensure(hp.twm.size() * sizeof(float2))) return rc;
+  CU(cudaMemcpyAsync(h->d_tw1.p, hp.tw1.data(), hp.tw1.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_tw2.p, hp.tw2.data(), hp.tw2.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_twm.p, hp.twm.data(), hp.twm.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->dp.N = hp.N; h->dp.N1 = hp.N1; h->dp.N2 = hp.N2;
+  fill_subplan(hp.s1, h->d_tw1.as<float2>(), h->dp.s1);
+  fill_subplan(hp.s2, h->d_tw2.as<float2>(), h->dp.s2);
+  h->dp.twm = h->d_twm.as<float2>();
+  h->hp = std::move(hp);
+  return 0;
+}
+
+size_t mid_smem(const DevPlan& p, bool with_q) {
+  return (size_t)(p.N1 * mid_sa(p.N2) + p.N2 * mid_sb(p.N1)) * sizeof(float2) + (with_q ? (size_t)p.N * sizeof(float) : 0);
+}
+size_t cols_smem(const DevPlan& p, bool with_q) {
+  return (size_t)p.N1 * kTileW * (sizeof(float2) + (with_q ? sizeof(float) : 0));
+}
+size_t rows_smem(const DevPlan& p) { return (size_t)p.N2 * kRowPitch * sizeof(float2); }
+
+template <class K> int allow_smem(gnssacq* h, K kern, size_t bytes) {
+  if (bytes > h->smem_optin) return fail(GNSSACQ_EINVAL, "transform does not fit in shared memory");
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+enum { kStageFwd = 0, kStageCorrRows = 1, kStageCorrCols = 2, kStageFinalize = 3 };
+
+cudaEvent_t take_event(gnssacq* h) {
+  if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct StageTimer {
+  gnssacq* h; int stage; int nl; cudaEvent_t a = nullptr;
+  StageTimer(gnssacq* h_, int stage_, int nl_) : h(h_), stage(stage_), nl(nl_) {
+    if (h->profiling) { a = take_event(h); cudaEventRecord(a, h->stream); }
+  }
+  ~StageTimer() {
+    if (a) {
+      cudaEvent_t b = take_event(h);
+      cudaEventRecord(b, h->stream);
+      h->spans.push_back({stage, a, b});
+      h->prof_launches[stage] += nl;
+    }
+  }
+};
+
+// Run f(integral_constant<RC>) for the plan's radix class.
+template <class F> int with_radix_class(int rc, F&& f) {
+  switch (rc) {
+    case 0: return f(std::integral_constant<int, 0>{});
+    case 1: return f(std::integral_constant<int, 1>{});
+    default: return f(std::integral_constant<int, 2>{});
+  }
+}
+
+// Forward transforms of `nt` inputs into X (position order). SRC 0: capture blocks with
+// wipe-off (nt = Dc*B, transform d*B+b); SRC 1: real replicas.
+template <int SRC>
+int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int B, int nt, float2* X) {
+  return with_radix_class(h->hp.rclass, [&](auto rc) -> int {
+    constexpr int RC = decltype(rc)::value;
+    const DevPlan& p = h->dp;
+    const float2* tab = h->d_nco_f32.as<float2>();
+    StageTimer timer(h, kStageFwd, h->hp.large ? 2 : 1);
+    if (!h->hp.large) {
+      const size_t sm = mid_smem(p, false);
+      auto kern = k_fwd_mid<RC, SRC>;
+      if (int rc2 = allow_smem(h, kern, sm)) return rc2;
+      GNSSACQ_LAUNCH(kern, dim3(nt), dim3(kThreads), sm, h->stream, p, h->d_x, rep, d_freq, tab, stride, B, X);
+      h->launches += 1;
+    } else {
+      const size_t smc = cols_smem(p, false), smr = rows_smem(p);
+      auto kc = k_fwd_cols<RC, SRC>;
+      auto kr = k_fwd_rows<RC>;
+      if (int rc2 = allow_smem(h, kc, smc)) return rc2;
+      if (int rc2 = allow_smem(h, kr, smr)) return rc2;
+      GNSSACQ_LAUNCH(kc, dim3((p.N2 + kTileW - 1) / kTileW, nt), dim3(kThreads), smc, h->stream,
+                     p, h->d_x, rep, d_freq, tab, stride, B, X);
+      GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, nt), dim3(kThreads), smr, h->stream, p, X);
+      h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return 0;
+  });
+}
+
+// Correlate one doppler chunk [d0, d0+dc) against all replicas.
+int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags, float scale, int ntiles, float* d_qdump) {
+  return with_radix_class(h->hp.rclass, [&](auto rc) -> int {
+    constexpr int RC = decltype(rc)::value;
+    const DevPlan& p = h->dp;
+    const int R = h->R;
+    if (!h->hp.large) {
+      const size_t sm = mid_smem(p, B > 1);
+      auto kern = k_corr_mid<RC>;
+      if (int rc2 = allow_smem(h, kern, sm)) return rc2;
+      StageTimer timer(h, kStageCorrCols, 1);
+      GNSSACQ_LAUNCH(kern, dim3(R * dc), dim3(kThreads), sm, h->stream, p, h->d_X.as<float2>(),
+                     h->d_C.as<float2>(), R, B, D, d0, n_lags, scale, h->d_parts.as<Part>(), d_qdump);
+      h->launches += 1;
+    } else {
+      const size_t smr = rows_smem(p), smc = cols_smem(p, B > 1);
+      auto kr = k_corr_rows<RC>;
+      auto kc = k_corr_cols<RC>;
+      if (int rc2 = allow_smem(h, kr, smr)) return rc2;
+      if (int rc2 = allow_smem(h, kc, smc)) return rc2;
+      const int units = R * dc;
+      for (int u0 = 0; u0 < units; u0 += Uc) {
+        const int uc = std::min(Uc, units - u0);
+        {
+          StageTimer timer(h, kStageCorrRows, 1);
+          GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, h->stream,
+                         p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
+        }
+        StageTimer timer(h, kStageCorrCols, 1);
+        GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, h->stream, p,
+                       h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
+                       h->d_parts.as<Part>(), d_qdump);
+        h->launches += 2;
+      }
+    }
+    CU(cudaGetLastError());
+    return 0;
+  });
+}
+
+int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int normalize, int n_lags,
+               Record* d_out, float* d_qdump) {
+  if (!h->d_x) return fail(GNSSACQ_ESTATE, "gnssacq_set_signal has not been called");
+  if (h->R <= 0) return fail(GNSSACQ_ESTATE, "gnssacq_set_replicas has not been called");
+  if (!nco_freq || D <= 0 || B <= 0 || stride < 0) return fail(GNSSACQ_EINVAL, "bad search arguments");
+  const int N = h->N, R = h->R;
+  if ((int64_t)(B - 1) * stride + N > h->n_x)
+    return fail(GNSSACQ_EINVAL, "capture too short: need (n_blocks-1)*block_stride + N = " +
+                                    std::to_string((int64_t)(B - 1) * stride + N) + " samples, have " + std::to_string(h->n_x));
+  if (n_lags <= 0 || n_lags > N) n_lags = N;
+  if (B > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
+  const DevPlan& p = h->dp;
+  const bool large = h->hp.large;
+  const int ntiles = large ? (p.N2 + kTileW - 1) / kTileW : 1;
+  const float scale = 1.0f / (float)N;
+  const size_t tbytes = (size_t)N * sizeof(float2);
+
+  if (int rc = h->d_freq.ensure((size_t)D * sizeof(double))) return rc;
+  CU(cudaMemcpyAsync(h->d_freq.p, nco_freq, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = h->d_parts.ensure((size_t)R * D * ntiles * sizeof(Part))) return rc;
+
+  int Dc = (int)std::max<size_t>(1, std::min<size_t>((size_t)D, kXChunkBytes / (tbytes * B)));
+  Dc = std::max(1, std::min(Dc, 65535 / B));
+  if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
+  int Uc = 0;
+  if (large) {
+    Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, kScratchBytes / (tbytes * B)));
+    Uc = std::min(Uc, 65535);
+    if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
+  }
+  for (int d0 = 0; d0 < D; d0 += Dc) {
+    const int dc = std::min(Dc, D - d0);
+    if (int rc = forward<0>(h, nullptr, h->d_freq.as<double>() + d0, stride, B, dc * B, h->d_X.as<float2>())) return rc;
+    if (int rc = correlate_chunk(h, B, D, d0, dc, Uc, n_lags, scale, ntiles, d_qdump)) return rc;
+  }
+  {
+    StageTimer timer(h, kStageFinalize, 1);
+    GNSSACQ_LAUNCH(k_finalize, dim3(R), dim3(128), 0, h->stream, h->d_parts.as<Part>(), D, ntiles, N, normalize, d_out);
+  }
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* gnssacq_last_error(void) { return g_err.c_str(); }
+
+int gnssacq_create(int device, gnssacq_t** out) {
+  if (!out) return fail(GNSSACQ_EINVAL, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(GNSSACQ_EINVAL, "no such CUDA device " + std::to_string(device));
+  CU(cudaSetDevice(device));
+  gnssacq* h = new (std::nothrow) gnssacq();
+  if (!h) return fail(GNSSACQ_ENOMEM, "out of host memory");
+  h->device = device;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(GNSSACQ_ECUDA, cudaGetErrorString(e)); }
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->stream = h->own_stream;
+  h->nco_c128.resize(2 * kNcoSize);
+  for (int k = 0; k < kNcoSize; ++k) {
+    const double th = (2.0 * M_PI * (double)k) * (1.0 / kNcoSize);
+    h->nco_c128[2 * k] = cos(th);
+    h->nco_c128[2 * k + 1] = sin(th);
+  }
+  if (int rc = upload_nco(h)) { gnssacq_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+int gnssacq_destroy(gnssacq_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_C, &h->d_X,
+                    &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp})
+    b->release();
+  for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int gnssacq_set_stream(gnssacq_t* h, void* cuda_stream) {
+  if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int gnssacq_set_nco_table(gnssacq_t* h, const double* table_c128) {
+  if (!h || !table_c128) return fail(GNSSACQ_EINVAL, "NULL argument");
+  CU(cudaSetDevice(h->device));
+  h->nco_c128.assign(table_c128, table_c128 + 2 * kNcoSize);
+  return upload_nco(h);
+}
+
+int gnssacq_set_signal(gnssacq_t* h, const float* iq, int64_t n) {
+  if (!h || !iq || n <= 0) return fail(GNSSACQ_EINVAL, "bad signal arguments");
+  CU(cudaSetDevice(h->device));
+  if (int rc = h->d_x_own.ensure((size_t)n * sizeof(float2))) return rc;
+  CU(cudaMemcpyAsync(h->d_x_own.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  h->d_x = h->d_x_own.as<float2>();
+  h->n_x = n;
+  return 0;
+}
+
+int gnssacq_set_signal_device(gnssacq_t* h, const void* dev_iq, int64_t n) {
+  if (!h || !dev_iq || n <= 0) return fail(GNSSACQ_EINVAL, "bad signal arguments");
+  h->d_x = static_cast<const float2*>(dev_iq);
+  h->n_x = n;
+  return 0;
+}
+
+static int replicas_from_device(gnssacq_t* h, const float* d_rep, int32_t R, int32_t N) {
+  if (int rc = upload_plan(h, N)) return rc;
+  if (int rc = h->d_C.ensure((size_t)R * N * sizeof(float2))) return rc;
+  h->R = 0; h->N = N;
+  // grid.y of the large path is limited to 65535 transforms per launch
+  for (int r0 = 0; r0 < R; r0 += 32768) {
+    const int rc_n = std::min(32768, R - r0);
+    if (int rc = forward<1>(h, d_rep + (size_t)r0 * N, nullptr, 0, 1, rc_n, h->d_C.as<float2>() + (size_t)r0 * N)) return rc;
+  }
+  h->R = R;
+  return 0;
+}
+
+int gnssacq_set_replicas(gnssacq_t* h, const float* replicas, int32_t R, int32_t N) {
+  if (!h || !replicas || R <= 0 || N <= 0) return fail(GNSSACQ_EINVAL, "bad replica arguments");
+  CU(cudaSetDevice(h->device));
+  const size_t nel = (size_t)R * N;
+  if (int rc = h->d_tmp.ensure(nel * sizeof(float))) return rc;
+  CU(cudaMemcpyAsync(h->d_tmp.p, replicas, nel * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return replicas_from_device(h, h->d_tmp.as<float>(), R, N);
+}
+
+int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32_t R, int32_t N) {
+  if (!h || !device_replicas || R <= 0 || N <= 0) return fail(GNSSACQ_EINVAL, "bad replica arguments");
+  CU(cudaSetDevice(h->device));
+  return replicas_from_device(h, static_cast<const float*>(device_replicas), R, N);
+}
+
+int gnssacq_set_profiling(gnssacq_t* h, int32_t on) {
+  if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
+  h->profiling = on != 0;
+  return 0;
+}
+
+int gnssacq_get_stage_times(gnssacq_t* h, double* ms4, int64_t* launches4, int32_t reset) {
+  if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& sp : h->spans) {
+    float ms = 0.f;
+#ifndef GNSSACQ_EMU_BUILD
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+#endif
+    h->prof_ms[sp.stage] += ms;
+    h->event_pool.push_back(sp.a);
+    h->event_pool.push_back(sp.b);
+  }
+  h->spans.clear();
+  for (int i = 0; i < 4; ++i) {
+    if (ms4) ms4[i] = h->prof_ms[i];
+    if (launches4) launches4[i] = h->prof_launches[i];
+    if (reset) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  }
+  return 0;
+}
+
+int gnssacq_search_device(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride, int32_t n_blocks,
+                          int32_t normalize, int32_t n_lags, void* device_records) {
+  if (!h || !device_records) return fail(GNSSACQ_EINVAL, "NULL argument");
+  CU(cudaSetDevice(h->device));
+  return run_search(h, nco_freq, D, block_stride, n_blocks, normalize, n_lags, static_cast<Record*>(device_records), nullptr);
+}
+
+int gnssacq_search(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride, int32_t n_blocks,
+                   int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin, float* q_dump) {
+  if (!h || !metric || !lag || !dbin) return fail(GNSSACQ_EINVAL, "NULL argument");
+  CU(cudaSetDevice(h->device));
+  if (h->R <= 0) return fail(GNSSACQ_ESTATE, "gnssacq_set_replicas has not been called");
+  if (int rc = h->d_rec.ensure((size_t)h->R * sizeof(Record))) return rc;
+  float* d_q = nullptr;
+  const size_t qn = (size_t)h->R * (size_t)std::max(D, 0) * h->N;
+  if (q_dump) {
+    if (int rc = h->d_q.ensure(qn * sizeof(float))) return rc;
+    d_q = h->d_q.as<float>();
+  }
+  if (int rc = run_search(h, nco_freq, D, block_stride, n_blocks, normalize, n_lags, h->d_rec.as<Record>(), d_q)) return rc;
+  std::vector<Record> rec(h->R);
+  CU(cudaMemcpyAsync(rec.data(), h->d_rec.p, rec.size() * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
+  if (q_dump) CU(cudaMemcpyAsync(q_dump, d_q, qn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->R; ++r) { metric[r] = rec[r].metric; lag[r] = rec[r].lag; dbin[r] = rec[r].dbin; }
+  return 0;
+}
+
+int gnssacq_mix(gnssacq_t* h, float* iq, int64_t n, double f, double p) {
+  if (!h || !iq || n < 0) return fail(GNSSACQ_EINVAL, "bad mix arguments");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  // dp = int(floor(p*NT*(1<<50))), df likewise (gnsstools/nco.py:33-34)
+  const double scale = (double)kNcoSize * (double)(1ll << 50);
+  const long long dp0 = (long long)floor(p * scale);
+  const long long df = (long long)floor(f * scale);
+  if (int rc = h->d_tmp.ensure((size_t)n * sizeof(float2))) return rc;
+  CU(cudaMemcpyAsync(h->d_tmp.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  const int blocks = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, 148 * 16);
+  GNSSACQ_LAUNCH(k_mix, dim3(blocks), dim3(kThreads), 0, h->stream, h->d_tmp.as<float2>(), (long long)n,
+                 (unsigned long long)dp0, (unsigned long long)df, h->d_nco_f64.as<double2>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(iq, h->d_tmp.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large) {
+  if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
+  if (N) *N = h->hp.N;
+  if (N1) *N1 = h->hp.N1;
+  if (N2) *N2 = h->hp.N2;
+  if (large) *large = h->hp.large ? 1 : 0;
+  return 0;
+}
+
+int64_t gnssacq_launch_count(gnssacq_t* h) { return h ? h->launches : 0; }
+
+int gnssacq_synchronize(gnssacq_t* h) {
+  if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

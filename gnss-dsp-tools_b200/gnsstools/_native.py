@@ -1,0 +1,190 @@
+"""ctypes binding of libgnssacq.so (include/gnssacq.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present,
+every entry point raises. ``Engine`` takes an optional already-loaded ``CDLL`` so the
+test-suite can inject its own build; the product path always goes through
+:func:`library`, which loads only the in-tree sm_100a library.
+"""
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgnssacq.so')
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    p, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.gnssacq_last_error.restype = C.c_char_p
+    lib.gnssacq_last_error.argtypes = []
+    sigs = {
+        'gnssacq_create': [C.c_int, C.POINTER(p)],
+        'gnssacq_destroy': [p],
+        'gnssacq_set_stream': [p, p],
+        'gnssacq_set_nco_table': [p, p],
+        'gnssacq_set_signal': [p, p, i64],
+        'gnssacq_set_signal_device': [p, p, i64],
+        'gnssacq_set_replicas': [p, p, i32, i32],
+        'gnssacq_set_replicas_device': [p, p, i32, i32],
+        'gnssacq_set_profiling': [p, i32],
+        'gnssacq_get_stage_times': [p, p, p, i32],
+        'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
+        'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
+        'gnssacq_mix': [p, p, i64, dbl, dbl],
+        'gnssacq_plan_info': [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        'gnssacq_synchronize': [p],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.gnssacq_launch_count.argtypes = [p]
+    lib.gnssacq_launch_count.restype = i64
+    return lib
+
+
+def library():
+    """The in-tree CUDA library; raises NativeError if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise NativeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                                  '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+            _lib = _declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+RECORD_DTYPE = np.dtype([('metric', np.float32), ('lag', np.int32), ('dbin', np.int32), ('pad', np.int32)])
+
+
+class Engine:
+    """One acquisition engine bound to one GPU (a gnssacq_t handle)."""
+
+    def __init__(self, device=0, lib=None):
+        self._lib = _declare(lib) if lib is not None else library()
+        self._h = C.c_void_p()
+        self._check(self._lib.gnssacq_create(int(device), C.byref(self._h)))
+        self.device = device
+        from . import nco as _nco
+        tab = np.ascontiguousarray(_nco.nco_table, dtype=np.complex128)
+        self._check(self._lib.gnssacq_set_nco_table(self._h, _ptr(tab)))
+        self.R = 0
+        self.N = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.gnssacq_last_error().decode('utf-8', 'replace')
+            if rc == -1:
+                raise ValueError(msg)
+            raise NativeError('gnssacq error %d: %s' % (rc, msg))
+
+    def close(self):
+        if self._h:
+            self._lib.gnssacq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.gnssacq_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def set_signal(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        self._check(self._lib.gnssacq_set_signal(self._h, _ptr(x), x.size))
+        self.n_samples = x.size
+
+    def set_signal_device(self, device_ptr, n_samples):
+        self._check(self._lib.gnssacq_set_signal_device(self._h, C.c_void_p(int(device_ptr)), int(n_samples)))
+        self.n_samples = int(n_samples)
+
+    def set_replicas(self, replicas):
+        rep = np.ascontiguousarray(replicas, dtype=np.float32)
+        if rep.ndim != 2:
+            raise ValueError('replicas must be R x N')
+        self._check(self._lib.gnssacq_set_replicas(self._h, _ptr(rep), rep.shape[0], rep.shape[1]))
+        self.R, self.N = rep.shape
+
+    def set_replicas_device(self, device_ptr, R, N):
+        self._check(self._lib.gnssacq_set_replicas_device(self._h, C.c_void_p(int(device_ptr)), int(R), int(N)))
+        self.R, self.N = int(R), int(N)
+
+    def set_profiling(self, on):
+        self._check(self._lib.gnssacq_set_profiling(self._h, int(bool(on))))
+
+    def stage_times(self, reset=True):
+        """{'fwd','corr_rows','corr','finalize'} -> (milliseconds, launches) since the last reset."""
+        ms = np.zeros(4, np.float64)
+        nl = np.zeros(4, np.int64)
+        self._check(self._lib.gnssacq_get_stage_times(self._h, _ptr(ms), _ptr(nl), int(bool(reset))))
+        names = ('fwd', 'corr_rows', 'corr', 'finalize')
+        return {k: (float(ms[i]), int(nl[i])) for i, k in enumerate(names)}
+
+    # -- search
+    def search(self, nco_freq, block_stride, n_blocks, normalize, n_lags=0, dump=False):
+        f = np.ascontiguousarray(nco_freq, dtype=np.float64)
+        D = f.size
+        metric = np.empty(self.R, np.float32)
+        lag = np.empty(self.R, np.int32)
+        dbin = np.empty(self.R, np.int32)
+        q = np.empty((self.R, D, self.N), np.float32) if dump else None
+        self._check(self._lib.gnssacq_search(self._h, _ptr(f), D, int(block_stride), int(n_blocks), int(bool(normalize)),
+                                             int(n_lags), _ptr(metric), _ptr(lag), _ptr(dbin),
+                                             _ptr(q) if dump else None))
+        return (metric, lag, dbin, q) if dump else (metric, lag, dbin)
+
+    def search_device(self, nco_freq, block_stride, n_blocks, normalize, n_lags, device_records_ptr):
+        f = np.ascontiguousarray(nco_freq, dtype=np.float64)
+        self._check(self._lib.gnssacq_search_device(self._h, _ptr(f), f.size, int(block_stride), int(n_blocks),
+                                                    int(bool(normalize)), int(n_lags),
+                                                    C.c_void_p(int(device_records_ptr))))
+
+    def mix(self, x, f, p):
+        if not (isinstance(x, np.ndarray) and x.dtype == np.complex64 and x.flags['C_CONTIGUOUS']):
+            raise TypeError('mix needs a contiguous complex64 array (as io.get_samples_complex returns)')
+        self._check(self._lib.gnssacq_mix(self._h, _ptr(x), x.size, float(f), float(p)))
+
+    def plan_info(self):
+        v = [C.c_int32() for _ in range(4)]
+        self._check(self._lib.gnssacq_plan_info(self._h, *[C.byref(a) for a in v]))
+        return dict(N=v[0].value, N1=v[1].value, N2=v[2].value, large=bool(v[3].value))
+
+    def launch_count(self):
+        return int(self._lib.gnssacq_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.gnssacq_synchronize(self._h))
+
+
+_default_engine = None
+
+
+def default_engine():
+    """Process-wide engine on the current device (LOCAL_RANK under torchrun, else 0)."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(int(os.environ.get('LOCAL_RANK', '0')))
+    return _default_engine
+
+
+def mix_inplace(x, f, p):
+    default_engine().mix(x, f, p)

@@ -1,0 +1,116 @@
+/* gnssacq.h — C ABI of libgnssacq.so, the B200 (sm_100a) FFT acquisition engine.
+ *
+ * The reference (pmonta/GNSS-DSP-tools) is pure Python and has no FFI: its hot path is the
+ * local search() function of each acquire-*.py script (acquire-gps-l1.py:18-40 and the
+ * variants listed in SURVEY.md §8a), fanned out over PRNs by worker()/mp.Pool
+ * (acquire-gps-l1.py:100-108). This header is the boundary that replaces that fan-out:
+ * one handle per GPU, one batched call for all replicas x Doppler bins. The ctypes binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success or a negative GNSSACQ_E* code;
+ * gnssacq_last_error() gives the message for the calling thread. Pointers are caller-owned
+ * host memory unless the name says "device". A handle is bound to one CUDA device and one
+ * stream; it is thread-compatible (one thread at a time per handle), with no global state.
+ */
+#ifndef GNSSACQ_H
+#define GNSSACQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gnssacq gnssacq_t;
+
+enum {
+  GNSSACQ_OK = 0,
+  GNSSACQ_EINVAL = -1,   /* bad argument (sizes, NULLs, unsupported FFT length) */
+  GNSSACQ_ECUDA = -2,    /* CUDA runtime error; message carries cudaGetErrorString */
+  GNSSACQ_ESTATE = -3,   /* call order: signal / replicas not set */
+  GNSSACQ_ENOMEM = -4
+};
+
+/* Per-replica result as produced on the device (16 bytes; the multi-GPU path all-gathers
+ * arrays of these). dbin indexes the nco_freq list of the call, -1 when no metric was > 0
+ * (the reference then returns (0,0,0), acquire-gps-l1.py:25,36-40). */
+typedef struct {
+  float metric;
+  int32_t lag;
+  int32_t dbin;
+  int32_t pad;
+} gnssacq_record_t;
+
+const char* gnssacq_last_error(void);
+
+/* Replaces the mp.Pool set-up of acquire-gps-l1.py:105-108: one engine per GPU. */
+int gnssacq_create(int device, gnssacq_t** out);
+int gnssacq_destroy(gnssacq_t* h);
+
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*),
+ * e.g. torch.cuda.current_stream().cuda_stream. NULL restores the handle's own stream. */
+int gnssacq_set_stream(gnssacq_t* h, void* cuda_stream);
+
+/* The 1024-entry complex128 phase table nco_table of gnsstools/nco.py:3-4, interleaved
+ * re,im. Optional: by default the library computes cos/sin(2*pi*k/1024) itself; the Python
+ * wrapper passes numpy's table so nco.mix is bit-identical to the reference. */
+int gnssacq_set_nco_table(gnssacq_t* h, const double* table_c128);
+
+/* The capture `x` that search(x, ...) receives (acquire-gps-l1.py:18): complex64,
+ * interleaved re,im, n_samples samples. Copied to the device. */
+int gnssacq_set_signal(gnssacq_t* h, const float* iq_c64, int64_t n_samples);
+/* Same, but borrow a device buffer (no copy); it must outlive the searches. */
+int gnssacq_set_signal_device(gnssacq_t* h, const void* device_iq_c64, int64_t n_samples);
+
+/* Time-domain replicas, R rows of N float32 (+-1, 0 in a zero-padded half; already
+ * BOC-modulated): what the reference feeds to fft.fft() at acquire-gps-l1.py:23-24,
+ * acquire-gps-l5i.py:23-24, acquire-galileo-e1b.py:24-26. N is the FFT length = number of
+ * lags searched. The replica spectra are computed on the device. */
+int gnssacq_set_replicas(gnssacq_t* h, const float* replicas, int32_t R, int32_t N);
+
+/* Same, from R*N float32 already resident on the device (no copy; read before return of
+ * the stream work, so keep it alive until the stream has drained). */
+int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32_t R, int32_t N);
+
+/* The Doppler x block loops of search() for every replica at once.
+ *   nco_freq[D]   wipe-off frequency per Doppler bin in cycles/sample, i.e. the float64
+ *                 value -doppler/fs (or -(562500*chan+doppler)/fs, acquire-glonass-l1.py:28)
+ *                 exactly as the reference computes it
+ *   block_stride  samples between the starts of consecutive non-coherent blocks
+ *                 (n for both circular and zero-padded variants; block length is N)
+ *   n_blocks      non-coherent sums ("ms", "ms//10", ... per script)
+ *   normalize     1: metric = q[idx]/mean(q) (acquire-gps-l1.py:35); 0: raw q[idx]
+ *   n_lags        argmax over lags [0, n_lags); pass N (or <= 0) for the reference behaviour
+ * Outputs, each R long: metric, lag (= idx of acquire-gps-l1.py:34), dbin (index into
+ * nco_freq, -1 if nothing exceeded 0). q_dump, if not NULL, receives the full R x D x N
+ * float32 grid of q (testing aid). Synchronous. */
+int gnssacq_search(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride,
+                   int32_t n_blocks, int32_t normalize, int32_t n_lags,
+                   float* metric, int32_t* lag, int32_t* dbin, float* q_dump);
+
+/* Same search, asynchronous on the handle's stream, writing R gnssacq_record_t to a device
+ * buffer (e.g. a torch tensor that is then all-gathered). nco_freq is read before return. */
+int gnssacq_search_device(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride,
+                          int32_t n_blocks, int32_t normalize, int32_t n_lags,
+                          void* device_records);
+
+/* nco.mix(x, f, p) of gnsstools/nco.py:30-41 on the GPU, in place on a host complex64
+ * buffer (copy in, mix, copy out). Bit-identical to the reference. */
+int gnssacq_mix(gnssacq_t* h, float* iq_c64, int64_t n_samples, double f, double p);
+
+/* Introspection for tests and the benchmark. */
+int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
+int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
+int gnssacq_synchronize(gnssacq_t* h);
+/* Per-stage device time: when profiling is on, CUDA events bracket the launches of each stage
+ * on the handle's stream. Stages: 0 wipe-off+forward FFT, 1 correlate rows kernel (large
+ * plans only), 2 correlate kernel (mid plans) / correlate columns kernel (large plans),
+ * 3 finalize. gnssacq_get_stage_times synchronises, then returns accumulated milliseconds
+ * and launch counts (4 entries each) and optionally resets them. */
+int gnssacq_set_profiling(gnssacq_t* h, int32_t on);
+int gnssacq_get_stage_times(gnssacq_t* h, double* ms4, int64_t* launches4, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNSSACQ_H */

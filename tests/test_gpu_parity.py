@@ -1,0 +1,173 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (ctypes), against the oracle
+on the same seeded inputs. Integer results (lag index, Doppler bin) must be bit-exact;
+the metric within 1e-4 relative (BASELINE.json north_star); the full q grid within 1e-5
+of its peak."""
+import numpy as np
+import pytest
+
+from oracle import acq_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+METRIC_RTOL = 1e-4      # north-star tolerance
+GRID_TOL = 1e-5         # |q_gpu - q_ref| <= GRID_TOL * max(q_ref)
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from gnsstools import _native
+    e = _native.Engine(0)
+    yield e
+    e.close()
+
+
+def random_chips(L, seed):
+    return np.random.default_rng(seed).integers(0, 2, L).astype(np.float64)
+
+
+def make_x(n, blocks, fs, chips, fd, phase, amp, seed, pad, boc=False):
+    rng = np.random.default_rng(seed)
+    nx = n * (blocks + (2 if pad else 1))
+    x = rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)
+    t = np.arange(nx)
+    L = len(chips)
+    c = orc.resample_code(chips, phase, 0, float(L) / n, nx)
+    if boc:
+        c = c * orc.boc11(phase, 0, float(L) / n, nx)
+    x += amp * c * np.exp(2j * np.pi * fd * t / fs)
+    return np.round(x).astype(np.complex64)
+
+
+# (id, L, fs, n, pad, boc, normalize, blocks, grid, nprn, lag_limit)   — one row per reference N / variant
+ENGINE_CASES = [
+    ('A-gps-l1-4096', 1023, 4096000.0, 4096, False, False, True, 3, (-5000, 5000, 500), 4, None),
+    ('A-xona-x5p-30690', 10230, 30690000.0, 30690, False, False, True, 2, (-600, 600, 200), 2, None),
+    ('B-glonass-16384', 511, 16384000.0, 16384, False, False, False, 2, (-600, 600, 200), 1, None),
+    ('C-l1c-81920-boc', 10230, 8192000.0, 81920, False, True, False, 2, (-60, 60, 20), 2, None),
+    ('D-b1i-2x8192', 2046, 8192000.0, 8192, True, False, False, 3, (-600, 600, 200), 3, None),
+    ('D-e1-2x32768-boc', 4092, 8192000.0, 32768, True, True, False, 1, (-150, 150, 50), 2, None),
+    ('D-l5-2x30690', 10230, 30690000.0, 30690, True, False, False, 3, (-600, 600, 200), 2, None),
+    ('D-e6-2x15345', 5115, 15345000.0, 15345, True, False, False, 2, (-600, 600, 200), 2, None),
+    ('D-l2cm-2x81920', 10230, 4096000.0, 81920, True, False, False, 1, (-40, 40, 20), 2, None),
+    ('cfg2-163680-10ms', 1023, 16368000.0, 163680, False, False, True, 1, (-500, 500, 250), 3, 16368),
+    ('cfg4-native-2x25000', 10230, 25000000.0, 25000, True, False, False, 4, (-400, 400, 200), 2, None),
+]
+
+
+@pytest.mark.parametrize('case', ENGINE_CASES, ids=[c[0] for c in ENGINE_CASES])
+def test_engine_matches_oracle(eng, case):
+    cid, L, fs, n, pad, boc, normalize, blocks, grid, nprn, lag_limit = case
+    chips = [random_chips(L, 100 + i) for i in range(nprn)]
+    fd = grid[0] + 1.4 * grid[2]
+    x = make_x(n, blocks, fs, chips[0], fd, 0.37 * L, 3.0, 7, pad, boc)
+    x64 = x.astype(np.complex128)
+    eng.set_signal(x)
+    eng.set_replicas(np.array([orc.replica(c, n, pad, boc) for c in chips]))
+    f = -orc.doppler_bins(grid) / fs
+    m, l, d, q = eng.search(f, n, blocks, normalize, n_lags=lag_limit or 0, dump=True)
+    for i, c in enumerate(chips):
+        ref, (idx, dbin, qg) = orc.search(x64, c, fs, n, grid, blocks, pad=pad, boc=boc, normalize=normalize,
+                                          return_grid=True, lag_limit=lag_limit)
+        assert (int(l[i]), int(d[i])) == (idx, dbin), (cid, i)
+        assert abs(m[i] - ref[0]) <= METRIC_RTOL * ref[0], (cid, i, m[i], ref[0])
+        assert np.max(np.abs(q[i] - qg)) <= GRID_TOL * np.max(qg), (cid, i)
+    # the planted replica is found at the planted Doppler bin
+    assert int(d[0]) == 1
+
+
+def test_config1_script_level(eng):
+    """BASELINE config 1 through the script-level API: acquire-gps-l1 PRN 1, 1 ms, +-5 kHz/500 Hz."""
+    from gnsstools import acquire, synth
+    import gnsstools.gps.ca as ca
+    x = synth.capture('gps-l1', ms=1, sats=[(1, 1500.0, 300.25, 4.0)], seed=1234)
+    grid = (-5000.0, 5000.0, 500.0)
+    got = acquire.acquire('gps-l1', x, list(range(1, 33)), grid, 1, engine=eng)
+    x64 = x.astype(np.complex128)
+    for prn, g in zip(range(1, 33), got):
+        want = orc.search_script('gps-l1', x64, ca.ca_code(prn), prn, grid, 1)
+        assert g[1] == want[1] and g[2] == want[2], (prn, g, want)
+        assert abs(g[0] - want[0]) <= METRIC_RTOL * want[0]
+    assert got[0][2] == 1500.0 and abs(got[0][1] - 300.25) < 0.5
+
+
+def test_golden_config1(eng):
+    """Against the reference's own output committed under tests/golden (made by make_golden.py)."""
+    import os
+    from gnsstools import acquire, synth
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'gps_l1_config1.npz'))
+    x = synth.capture('gps-l1', ms=int(g['ms']), sats=[(1, 1500.0, 300.25, 4.0)], seed=int(g['seed']))
+    assert np.array_equal(x, g['x'])
+    got = acquire.acquire('gps-l1', x, [int(p) for p in g['prns']], tuple(g['grid']), int(g['ms']), engine=eng)
+    for i, r in enumerate(got):
+        assert r[1] == g['code'][i] and r[2] == g['doppler'][i]
+        assert abs(r[0] - g['metric'][i]) <= METRIC_RTOL * g['metric'][i]
+
+
+def test_mix_bit_exact(eng):
+    rng = np.random.default_rng(11)
+    n = 5_998_629            # 69.984 MHz x 85 ms + change, odd on purpose
+    a = (rng.integers(-127, 128, n) + 1j * rng.integers(-127, 128, n)).astype(np.complex64)
+    b = a.copy()
+    eng.mix(a, -9334875.0 / 69984000.0, 0.0)
+    orc.mix(b, -9334875.0 / 69984000.0, 0.0)
+    assert np.array_equal(a, b)
+
+
+def test_all_zero_and_short_inputs(eng):
+    n = 4096
+    eng.set_signal(np.zeros(2 * n, np.complex64))
+    eng.set_replicas(orc.replica(random_chips(1023, 1), n, False, False)[None, :])
+    m, l, d = eng.search(np.array([0.0, 1e-4]), n, 1, True)
+    assert d[0] == -1 and m[0] == 0.0
+    with pytest.raises(ValueError):
+        eng.search(np.array([0.0]), n, 3, True)     # needs 3 blocks, capture holds 2
+    with pytest.raises(ValueError):
+        eng.set_replicas(np.ones((1, 2 * 37), np.float32))
+
+
+def test_batch_invariance_and_determinism(eng):
+    """Results for a PRN do not depend on which other PRNs share the batch, nor on the run."""
+    n, fs = 4096, 4096000.0
+    chips = [random_chips(1023, 40 + i) for i in range(8)]
+    x = make_x(n, 4, fs, chips[2], 700.0, 111.0, 2.0, 3, False)
+    eng.set_signal(x)
+    f = -orc.doppler_bins((-2000, 2000, 100)) / fs
+    eng.set_replicas(np.array([orc.replica(c, n, False, False) for c in chips]))
+    full = [np.copy(a) for a in eng.search(f, n, 4, True)]
+    again = eng.search(f, n, 4, True)
+    for a, b in zip(full, again):
+        assert np.array_equal(a, b)
+    eng.set_replicas(np.array([orc.replica(c, n, False, False) for c in chips[2:5]]))
+    sub = eng.search(f, n, 4, True)
+    for a, b in zip(full, sub):
+        assert np.array_equal(a[2:5], b)
+
+
+def test_full_size_config2_property(eng):
+    """BASELINE config 2 at full size (32 PRN x 80 Doppler x 163680 lags): too big for the
+    oracle in a test, so check the domain property — every planted satellite is recovered at
+    its planted Doppler bin and code phase, and sharding the Doppler grid in two halves and
+    merging with the reference's strict-'>' rule reproduces the single-call answer exactly."""
+    from gnsstools import acquire, synth
+    import gnsstools.gps.ca as ca
+    sig = acquire.Signal('gps.ca', 16368000.0, 163680, lambda ms: ms // 10, normalize=True, mod_L=True, periods=10)
+    planted = [(3, -7250.0, 100.0, 1.5), (11, 2500.0, 511.5, 1.5), (22, 9750.0, 1000.25, 1.5), (30, -250.0, 3.0, 1.5)]
+    x = synth.capture(sig, ms=10, sats=planted, seed=2, extra_ms=0)
+    grid = (-10000.0, 10000.0, 250.0)
+    prns = list(range(1, 33))
+    res = acquire.acquire(sig, x, prns, grid, 10, engine=eng, lag_limit=16368)
+    for prn, fd, phase, _ in planted:
+        metric, code, doppler = res[prn - 1]
+        assert doppler == fd, (prn, doppler)
+        assert abs(code - phase) < 0.1, (prn, code)
+        assert metric > 5.0
+    # Doppler sharding (what the multi-GPU path does), merged on the host
+    bins = acquire.doppler_bins(grid)
+    f = -bins / sig.fs
+    m0, l0, d0 = [np.copy(a) for a in eng.search(f[:40], sig.n, 1, True, 16368)]
+    m1, l1, d1 = eng.search(f[40:], sig.n, 1, True, 16368)
+    mf, lf, df = eng.search(f, sig.n, 1, True, 16368)
+    take1 = m1 > m0
+    assert np.array_equal(np.where(take1, m1, m0), mf)
+    assert np.array_equal(np.where(take1, l1, l0), lf)
+    assert np.array_equal(np.where(take1, d1 + 40, d0), df)
