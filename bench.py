@@ -203,7 +203,11 @@ def main():
     my_f = np.ascontiguousarray(freqs[my])
 
     eng = _native.Engine(local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch and the engine, so torch's CUDA events
+    # and NCCL calls are ordered with the engine's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.set_profiling(True)
 

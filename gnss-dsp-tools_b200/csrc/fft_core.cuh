@@ -215,6 +215,89 @@ __device__ __forceinline__ void stage_tile(float2* tile, int WP, int ncols, int 
   }
 }
 
+// Large odd prime radix (31): the symmetric-sum butterfly needs ~4P live registers in one
+// thread, which would cap the whole kernel at one CTA per SM. Instead two warps share each
+// butterfly: both load all P inputs and form the a/b halves, then the even warp produces
+// outputs {0, 1..K0, P-1..P-K0} and the odd warp the rest — no exchange, half the
+// accumulators each. A block barrier separates the loads from the in-place stores.
+template <int P, int K0, int K1, class Emit>
+__device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, const float2* b, Emit&& emit) {
+  constexpr int H = (P - 1) / 2;
+  static_for<K0, K1 + 1>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    float2 re = x0, im = make_float2(0.f, 0.f);
+    static_for<1, H + 1>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      constexpr float c = kTrig<P>.c[(j * k) % P];
+      constexpr float sn = kTrig<P>.s[(j * k) % P];
+      re.x += c * a[j].x; re.y += c * a[j].y;
+      im.x += sn * b[j].x; im.y += sn * b[j].y;
+    });
+    emit(k, make_float2(re.x + im.y, re.y - im.x));
+    emit(P - k, make_float2(re.x - im.y, re.y + im.x));
+  });
+}
+
+template <int P, bool INV>
+__device__ __forceinline__ void stage_tile_split(float2* tile, int WP, int ncols, int F, int m,
+                                                 const float2* __restrict__ tw) {
+  constexpr int H = (P - 1) / 2;
+  constexpr int KA = (H + 1) / 2;            // even warp: k = 1..KA (+ output 0); odd warp: KA+1..H
+  const int tc = threadIdx.x & (kTW - 1);
+  const int warp = threadIdx.x >> 5;
+  const int role = warp & 1;
+  const int slot = (warp >> 1) * 2 + ((threadIdx.x >> 4) & 1);
+  const int nslots = blockDim.x >> 5;        // butterflies in flight per round
+  const int nbf = F / P;
+  const int twstep = F / (P * m);
+  const int estride = m * WP;
+  const int rounds = (nbf + nslots - 1) / nslots;
+  for (int c0 = 0; c0 < ncols; c0 += kTW)    // uniform trip counts: every thread meets every barrier
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int bf = rd * nslots + slot;
+    const bool active = bf < nbf && c0 + tc < ncols;
+    const int blk = bf / m;
+    const int i = bf - blk * m;
+    float2* p = tile + (blk * P * m + i) * WP + c0 + tc;
+    const int twi = i * twstep;
+    float2 a[H + 1], b[H + 1];
+    float2 x0 = make_float2(0.f, 0.f);
+    auto in = [&](int q) -> float2 {
+      float2 v = p[q * estride];
+      if (INV) {
+        if (m > 1 && q > 0) v = cmulc(v, __ldg(&tw[q * twi]));
+        v = cswap(v);
+      }
+      return v;
+    };
+    if (active) {
+      x0 = in(0);
+      static_for<1, H + 1>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const float2 u = in(j), w = in(P - j);
+        a[j] = cadd(u, w);
+        b[j] = csub(u, w);
+      });
+    }
+    __syncthreads();                         // every input read before any in-place store
+    if (active) {
+      auto emit = [&](int q, float2 v) {
+        if (INV) v = cswap(v);
+        else if (m > 1 && q > 0) v = cmul(v, __ldg(&tw[q * twi]));
+        p[q * estride] = v;
+      };
+      if (role == 0) {
+        float2 s0 = x0;
+        static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
+        emit(0, s0);
+        prime_outputs<P, 1, KA>(x0, a, b, emit);
+      } else {
+        prime_outputs<P, KA + 1, H>(x0, a, b, emit);
+      }
+    }
+  }
+}
+
 // Radix classes: kernels are instantiated per class so that power-of-two plans are not
 // register-allocated for the 31-point butterfly. 0: {2,4,8,16}; 1: + {3,5}; 2: + {7,11,13,31}.
 constexpr int kNumRadixClasses = 3;
@@ -244,7 +327,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float2* tile, int WP, int 
                 case 7: stage_tile<7, INV>(tile, WP, ncols, F, m, tw); break;
                 case 11: stage_tile<11, INV>(tile, WP, ncols, F, m, tw); break;
                 case 13: stage_tile<13, INV>(tile, WP, ncols, F, m, tw); break;
-                case 31: stage_tile<31, INV>(tile, WP, ncols, F, m, tw); break;
+                case 31: stage_tile_split<31, INV>(tile, WP, ncols, F, m, tw); break;
                 default: break;   // the host planner never emits other radices
               }
             }

@@ -129,7 +129,8 @@ size_t rows_smem(const DevPlan& p) { return (size_t)p.N2 * kRowPitch * sizeof(fl
 
 template <class K> int allow_smem(gnssacq* h, K kern, size_t bytes) {
   if (bytes > h->smem_optin) return fail(GNSSACQ_EINVAL, "transform does not fit in shared memory");
-  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // static shared memory (reduction scratch) counts against the 48 KB default too
+  if (bytes > 40 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
 

@@ -101,7 +101,7 @@ __host__ __device__ __forceinline__ int mid_sb(int N1) { return N1 | 1; }
 // doppler d, wipe-off fused into the load). SRC 1: transform t = replica t (real input).
 // Output: X[t*N + p2*N1 + p1], "position" order.
 template <int RC, int SRC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_fwd_mid(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ rep,
           const double* __restrict__ freq, const float2* __restrict__ nco_tab,
           int stride, int B, float2* __restrict__ X) {
@@ -136,7 +136,7 @@ k_fwd_mid(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ re
 // grid.x = R * Dc; CTA (r, dd) loops over the B non-coherent blocks.
 // X: [Dc][B][N] capture spectra, C: [R][N] replica spectra (both position order).
 template <int RC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_corr_mid(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
            int R, int B, int D, int d0, int n_lags, float scale,
            Part* __restrict__ parts, float* __restrict__ q_dump) {
@@ -196,7 +196,7 @@ constexpr int kRowPitch = kTileW + 1;
 
 // grid = (ceil(N2/16), transforms). Load (+wipe-off), column FFT, four-step twiddle, store.
 template <int RC, int SRC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_fwd_cols(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ rep,
            const double* __restrict__ freq, const float2* __restrict__ nco_tab,
            int stride, int B, float2* __restrict__ X) {
@@ -225,7 +225,7 @@ k_fwd_cols(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ r
 
 // grid = (ceil(N1/16), transforms). In-place row FFTs on X.
 template <int RC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_fwd_rows(DevPlan pl, float2* __restrict__ X) {
   GNSSACQ_DYN_SMEM(float2, tile);
   const int N = pl.N, N1 = pl.N1, N2 = pl.N2;
@@ -246,7 +246,7 @@ k_fwd_rows(DevPlan pl, float2* __restrict__ X) {
 // grid = (ceil(N1/16), B, units). unit u -> replica r = (u0+u) % R, doppler dd = (u0+u) / R.
 // Multiply by the replica spectrum, inverse row FFT, conjugate four-step twiddle -> scratch.
 template <int RC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_corr_rows(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
             int R, int B, int u0, float2* __restrict__ scratch) {
   GNSSACQ_DYN_SMEM(float2, tile);
@@ -276,7 +276,7 @@ k_corr_rows(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__
 // grid = (ceil(N2/16), units). Inverse column FFT of every block, |.|, non-coherent sum,
 // per-tile max/argmax/sum. Shared memory: tile[N1][16] float2 (+ q[N1][16] float if B > 1).
 template <int RC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D, int d0, int u0,
             int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
   GNSSACQ_DYN_SMEM(float2, tile);
@@ -361,7 +361,7 @@ k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normali
 // In-place whole-capture carrier wipe-off, reference gnsstools/nco.py:30-41: int64 phase
 // accumulator scaled by 2^50 (closed form dp_i = dp0 + i*df, wrapping), complex128 table,
 // complex128 product rounded to complex64 on store.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_mix(float2* __restrict__ x, long long n, unsigned long long dp0, unsigned long long df,
       const double2* __restrict__ tab) {
   const long long stride = (long long)gridDim.x * blockDim.x;
