@@ -1,12 +1,9 @@
 """GPS L1 C/A code (IS-GPS-200): G1 xor delayed G2, 1023 chips, PRN 1-210.
-
-Mirrors the surface of reference gnsstools/gps/ca.py (chip_rate, code_length,
-codes, ca_code, code, first_10_chips).
-"""
+Surface of reference gnsstools/gps/ca.py (chip_rate, code_length, g2_delay, codes, ca_code, code)."""
 
 import numpy as np
 
-from .._codegen import resample, lfsr_fibonacci
+from .. import _codegen as _g
 
 chip_rate = 1023000
 code_length = 1023
@@ -31,8 +28,8 @@ _G2_DELAY = (
 g2_delay = {prn: d for prn, d in enumerate(_G2_DELAY, start=1)}
 
 # G1: 1 + x^3 + x^10 ; G2: 1 + x^2 + x^3 + x^6 + x^8 + x^9 + x^10 ; all-ones start.
-g1 = lfsr_fibonacci(10, (2, 9), [1] * 10, code_length)
-g2 = lfsr_fibonacci(10, (1, 2, 5, 7, 8, 9), [1] * 10, code_length)
+g1 = _g.lfsr_fibonacci(10, (2, 9), 0x3ff, code_length)
+g2 = _g.lfsr_fibonacci(10, (1, 2, 5, 7, 8, 9), 0x3ff, code_length)
 
 codes = {}
 
@@ -45,7 +42,12 @@ def ca_code(prn):
 
 
 def code(prn, chips, frac, incr, n):
-    return resample(ca_code(prn), chips, frac, incr, n)
+    return _g.resample(ca_code(prn), chips, frac, incr, n)
+
+
+def correlate(x, prn, chips, frac, incr, c):
+    """Tracking correlator (out of the acquisition path); see _codegen.correlate_plain."""
+    return _g.correlate_plain(x, chips, frac, incr, c, code_length)
 
 
 def first_10_chips(prn):

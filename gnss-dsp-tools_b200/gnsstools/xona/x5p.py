@@ -1,0 +1,33 @@
+"""Xona Pulsar X5P memory code (10230 chips), tabulated per PRN in the ICD and carried bit-packed in
+_data/memory_codes.npz. Surface of reference gnsstools/xona/x5p.py."""
+
+import numpy as np
+
+from .. import _codegen as _g
+
+chip_rate = 10230000
+code_length = 10230
+
+secondary_code = 1.0 - 2.0 * np.array([int(b) for b in _g.icd_table('xona.x5p', 'secondary_bits')[0]], dtype=np.float64)
+
+_table = None
+codes = {}
+
+
+def x5p_code(prn):
+    """0/1 chips; KeyError for a PRN the ICD does not define."""
+    global _table
+    if prn not in codes:
+        if _table is None:
+            _table = _g.memory_codes('xona.x5p')
+        codes[prn] = _table[prn]
+    return codes[prn]
+
+
+def code(prn, chips, frac, incr, n):
+    return _g.resample(x5p_code(prn), chips, frac, incr, n)
+
+
+def correlate(x, prn, chips, frac, incr, c):
+    """Tracking correlator (out of the acquisition path); see _codegen.correlate_plain."""
+    return _g.correlate_plain(x, chips, frac, incr, c, code_length)
