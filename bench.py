@@ -156,21 +156,6 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def merge_records(all_rec, d_per_rank):
-    """Rank-ordered strict-'>' merge of per-rank per-PRN records -> global (metric, lag, dbin).
-    Ranks hold ascending contiguous Doppler ranges, so ties go to the lowest Doppler bin
-    exactly as the single-GPU scan (acquire-gps-l1.py:36)."""
-    world = all_rec.shape[0]
-    best = all_rec[0].copy()
-    for k in range(1, world):
-        rec = all_rec[k]
-        take = (rec['dbin'] >= 0) & (rec['metric'] > best['metric'])
-        shifted = rec.copy()
-        shifted['dbin'] = np.where(rec['dbin'] >= 0, rec['dbin'] + k * d_per_rank, -1)
-        best = np.where(take, shifted, best)
-    return best
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -186,6 +171,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gnsstools import _native
+    from gnsstools import distributed as gd
 
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -283,7 +269,7 @@ def main():
     # ---- correctness of what was just timed: planted satellites recovered
     rec = rec_pin_all.numpy().view(_native.RECORD_DTYPE).reshape(world, R) if world > 1 else \
         rec_pin.numpy().view(_native.RECORD_DTYPE).reshape(1, R)
-    best = merge_records(rec, D_PER_GPU)
+    best = gd.merge_records(rec, [k * D_PER_GPU for k in range(world)])
     found = 0
     for prn, fd, phase, _ in sats:
         b = best[prn - 1]
