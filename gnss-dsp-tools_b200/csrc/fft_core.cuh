@@ -31,8 +31,42 @@ struct SubPlan {
 
 // ---------------------------------------------------------------- complex helpers
 __host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+// Packed FP32x2 arithmetic (sm_100a FFMA2 / FADD2 / FMUL2): one issue slot per complex
+// add or real-times-complex FMA instead of two. Same IEEE results as the scalar forms.
+#if defined(__CUDA_ARCH__) && !defined(GNSSACQ_NO_F32X2)
+__device__ __forceinline__ unsigned long long c2u(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 u2c(unsigned long long a) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+  return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c2u(a)), "l"(c2u(b)));
+  return u2c(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c2u(a)), "l"(c2u(b)));
+  return u2c(r);
+}
+// acc + s * a  (s real)
+__device__ __forceinline__ float2 cfma_real(float s, float2 a, float2 acc) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(c2u(make_float2(s, s))), "l"(c2u(a)), "l"(c2u(acc)));
+  return u2c(r);
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cfma_real(float s, float2 a, float2 acc) {
+  return make_float2(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y));
+}
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -153,8 +187,8 @@ template <int P> struct Dft {
         constexpr int j = decltype(J)::value;
         constexpr float c = kTrig<P>.c[(j * k) % P];
         constexpr float s = kTrig<P>.s[(j * k) % P];
-        re.x += c * a[j].x; re.y += c * a[j].y;
-        im.x += s * b[j].x; im.y += s * b[j].y;
+        re = cfma_real(c, a[j], re);
+        im = cfma_real(s, b[j], im);
       });
       v[k] = make_float2(re.x + im.y, re.y - im.x);        // re - i*im
       v[P - k] = make_float2(re.x - im.y, re.y + im.x);    // re + i*im
@@ -230,8 +264,8 @@ __device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, 
       constexpr int j = decltype(J)::value;
       constexpr float c = kTrig<P>.c[(j * k) % P];
       constexpr float sn = kTrig<P>.s[(j * k) % P];
-      re.x += c * a[j].x; re.y += c * a[j].y;
-      im.x += sn * b[j].x; im.y += sn * b[j].y;
+      re = cfma_real(c, a[j], re);
+      im = cfma_real(sn, b[j], im);
     });
     emit(k, make_float2(re.x + im.y, re.y - im.x));
     emit(P - k, make_float2(re.x - im.y, re.y + im.x));
