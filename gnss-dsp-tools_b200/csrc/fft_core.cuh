@@ -26,7 +26,10 @@ struct SubPlan {
   int ns;                   // number of stages
   int radix[kMaxStages];    // radix of stage j (forward order)
   int m[kMaxStages];        // element stride of stage j = product of the later radices
-  const float2* tw;         // device table: tw[k] = exp(-2*pi*i*k/F), k < F
+  const float2* tw;         // device table: tw[k] = exp(-2*pi*i*k/F), k < F, followed by the
+                            // per-stage tables below
+  int tws_off[kMaxStages];  // stage j twiddles, butterfly-major: tw[tws_off[j] + i*(R-1) + (q-1)]
+                            //   = exp(-2*pi*i * q*i / (R*m)),  i < m, 1 <= q < R   (0 if m == 1)
 };
 
 // ---------------------------------------------------------------- complex helpers

@@ -15,6 +15,7 @@ constexpr int kMidMax = 8192;        // N <= kMidMax: whole transform resident i
 struct HostSubPlan {
   int F = 0;
   std::vector<int> radix, m;
+  std::vector<int> tws_off;          // offset of each stage's butterfly-major twiddle table
   std::vector<int> pos_of_freq;      // position of frequency k after the forward transform
   std::vector<int> freq_of_pos;
 };
@@ -73,11 +74,24 @@ inline bool make_subplan(int F, HostSubPlan& sp) {
   return true;
 }
 
-inline std::vector<float2> unit_roots(int F) {
+// W_F^k for k < F, then one butterfly-major table per stage (see SubPlan::tws_off).
+inline std::vector<float2> unit_roots(HostSubPlan& sp) {
+  const int F = sp.F;
   std::vector<float2> t(F);
   for (int k = 0; k < F; ++k) {
     double a = -2.0 * M_PI * (double)k / (double)F;
     t[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  sp.tws_off.assign(sp.radix.size(), 0);
+  for (size_t j = 0; j < sp.radix.size(); ++j) {
+    const int R = sp.radix[j], m = sp.m[j];
+    if (m == 1) continue;
+    sp.tws_off[j] = (int)t.size();
+    for (int i = 0; i < m; ++i)
+      for (int q = 1; q < R; ++q) {
+        double a = -2.0 * M_PI * (double)((long long)q * i) / (double)(R * m);
+        t.push_back(make_float2((float)cos(a), (float)sin(a)));
+      }
   }
   return t;
 }
@@ -104,8 +118,8 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err) {
   if (!make_subplan(pl.N1, pl.s1) || !make_subplan(pl.N2, pl.s2)) { err = "unsupported factorisation"; return false; }
   for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
-  pl.tw1 = unit_roots(pl.N1);
-  pl.tw2 = unit_roots(pl.N2);
+  pl.tw1 = unit_roots(pl.s1);
+  pl.tw2 = unit_roots(pl.s2);
   pl.twm.resize((size_t)N);
   for (int p1 = 0; p1 < pl.N1; ++p1) {
     const long long k1 = pl.s1.freq_of_pos[p1];

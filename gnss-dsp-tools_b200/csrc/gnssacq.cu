@@ -1,7 +1,7 @@
 // libgnssacq.so — C ABI (include/gnssacq.h) over the sm_100a acquisition kernels.
 #include "../../include/gnssacq.h"
 #include "fft_plan.h"
-#include "kernels.cuh"
+#include "kernels_spec.cuh"
 
 #include <algorithm>
 #include <new>
@@ -70,6 +70,7 @@ struct gnssacq {
 
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
+  bool use_spec = true;               // plan-specialised correlate kernels when one matches
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -95,7 +96,11 @@ int upload_nco(gnssacq* h) {
 void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
   sp.F = hs.F;
   sp.ns = (int)hs.radix.size();
-  for (int j = 0; j < kMaxStages; ++j) { sp.radix[j] = j < sp.ns ? hs.radix[j] : 1; sp.m[j] = j < sp.ns ? hs.m[j] : 1; }
+  for (int j = 0; j < kMaxStages; ++j) {
+    sp.radix[j] = j < sp.ns ? hs.radix[j] : 1;
+    sp.m[j] = j < sp.ns ? hs.m[j] : 1;
+    sp.tws_off[j] = j < sp.ns ? hs.tws_off[j] : 0;
+  }
   sp.tw = tw;
 }
 
@@ -213,8 +218,10 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
       h->launches += 1;
     } else {
       const size_t smr = rows_smem(p), smc = cols_smem(p, B > 1);
-      auto kr = k_corr_rows<RC>;
-      auto kc = k_corr_cols<RC>;
+      corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2) : nullptr;
+      corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1) : nullptr;
+      if (!kr) kr = k_corr_rows<RC>;
+      if (!kc) kc = k_corr_cols<RC>;
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
       if (int rc2 = allow_smem(h, kc, smc)) return rc2;
       const int units = R * dc;
@@ -388,6 +395,12 @@ int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32
   return replicas_from_device(h, static_cast<const float*>(device_replicas), R, N);
 }
 
+int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
+  if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
+  if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
+  return fail(GNSSACQ_EINVAL, std::string("unknown option ") + name);
+}
+
 int gnssacq_set_profiling(gnssacq_t* h, int32_t on) {
   if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
   h->profiling = on != 0;
@@ -474,6 +487,12 @@ int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_
 }
 
 int64_t gnssacq_launch_count(gnssacq_t* h) { return h ? h->launches : 0; }
+
+int gnssacq_kernel_variant(gnssacq_t* h) {
+  if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
+  if (!h->hp.large || !h->use_spec) return 0;
+  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1) ? 2 : 0);
+}
 
 int gnssacq_synchronize(gnssacq_t* h) {
   if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");

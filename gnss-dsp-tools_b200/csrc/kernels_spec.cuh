@@ -1,0 +1,305 @@
+// Plan-specialised correlate kernels for the transform lengths GNSS receivers actually use.
+//
+// Same algorithm and data layout as the runtime-planned k_corr_rows / k_corr_cols
+// (kernels.cuh), but the radix schedule of the tile transform is a template parameter, so
+// strides, trip counts and twiddle offsets are immediates, and the first / last butterfly
+// stages are fused with the global-memory traffic around them:
+//   rows kernel: [load X, C -> multiply -> first inverse stage] -> smem stages ->
+//                [last inverse stage -> conjugate four-step twiddle -> coalesced store]
+//   cols kernel: [coalesced load -> first inverse stage] -> smem stages ->
+//                [last inverse stage -> |.| -> non-coherent sum -> max/argmax/sum]
+// Lengths without a specialisation run the generic kernels; results agree to rounding.
+#pragma once
+#include "kernels.cuh"
+
+namespace acq {
+
+// Radix schedule of one tile transform, forward order (as fft_plan.h builds it).
+template <int F_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+struct Sub {
+  static constexpr int F = F_;
+  static constexpr int NS = R1_ == 1 ? 1 : (R2_ == 1 ? 2 : (R3_ == 1 ? 3 : 4));
+  static_assert(R0_ * R1_ * R2_ * R3_ == F_, "radices must multiply to F");
+  static_assert(NS >= 2, "specialised kernels need at least two stages");
+  __host__ __device__ static constexpr int radix(int j) { return j == 0 ? R0_ : (j == 1 ? R1_ : (j == 2 ? R2_ : R3_)); }
+  __host__ __device__ static constexpr int stride(int j) {      // product of the later radices
+    int m = 1;
+    for (int k = j + 1; k < 4; ++k) m *= radix(k);
+    return m;
+  }
+};
+
+constexpr bool is_split_radix(int R) { return R >= 17; }
+
+// ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs
+template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
+  Dft<R>::run(v);
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
+}
+
+// ---- one in-shared-memory inverse stage (stage J of S), tile pitch WP, ncols live columns
+template <class S, int J, int WP>
+__device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const float2* __restrict__ twbase, int twoff) {
+  constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
+  const int tc = threadIdx.x & (kTW - 1);
+  if constexpr (is_split_radix(R)) {
+    stage_tile_split<R, true>(tile, WP, ncols, S::F, m, twbase);      // warp-pair version, W_F table
+  } else {
+    const int tb = threadIdx.x / kTW;
+    constexpr int nb = kThreads / kTW;
+    const float2* tws = twbase + twoff;
+    if (tc < ncols) {
+#pragma unroll 2
+      for (int bf = tb; bf < nbf; bf += nb) {
+        const int blk = bf / m, i = bf - blk * m;
+        float2* p = tile + (blk * R * m + i) * WP + tc;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = p[q * m * WP];
+        if constexpr (m > 1) {
+          const float2* w = tws + i * (R - 1);
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+        }
+        inv_dft<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) p[q * m * WP] = v[q];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class S, int J, int JEND, int WP>
+__device__ __forceinline__ void inv_stages_smem(float2* tile, int ncols, const SubPlan& sp) {
+  if constexpr (J >= JEND) {
+    inv_stage_smem<S, J, WP>(tile, ncols, sp.tw, sp.tws_off[J]);
+    inv_stages_smem<S, J - 1, JEND, WP>(tile, ncols, sp);
+  }
+}
+
+// =========================================================================== rows kernel
+// grid = (ceil(N1/16), B, units), as k_corr_rows. S = schedule of the length-N2 transform.
+template <class S>
+__global__ void __launch_bounds__(kThreads, 2)
+k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
+              int R_, int B, int u0, float2* __restrict__ scratch) {
+  GNSSACQ_DYN_SMEM(float2, tile);
+  constexpr int N2 = S::F, WP = kRowPitch, NS = S::NS;
+  const int N = pl.N, N1 = pl.N1;
+  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
+  constexpr int nb = kThreads / kTW;
+  const int row0 = blockIdx.x * kTileW;
+  const int nrows = imin(kTileW, N1 - row0);
+  const int b = blockIdx.y, ul = blockIdx.z, u = u0 + ul;
+  const int r = u % R_, dd = u / R_;
+  const float2* Cr = C + (long long)r * N;
+  const float2* Xb = X + ((long long)dd * B + b) * N;
+
+  // ---- first inverse stage (last forward stage, unit stride) fused with load + multiply
+  {
+    constexpr int R = S::radix(NS - 1), nbf = N2 / R;
+    if (tc < nrows) {
+      const int rowoff = (row0 + tc) * N2;
+#pragma unroll 2
+      for (int bf = tb; bf < nbf; bf += nb) {
+        const int g = rowoff + bf * R;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = cmulc(__ldg(&Cr[g + q]), __ldg(&Xb[g + q]));
+        inv_dft<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) tile[(bf * R + q) * WP + tc] = v[q];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- middle stages in shared memory
+  inv_stages_smem<S, NS - 2, 1, WP>(tile, nrows, pl.s2);
+  // ---- last inverse stage (first forward stage, stride m0)
+  float2* out = scratch + ((long long)ul * B + b) * N;
+  constexpr int R0 = S::radix(0), m0 = S::stride(0);
+  if constexpr (!is_split_radix(R0) && m0 >= 16) {
+    // fused with the conjugate four-step twiddle and the store: lanes walk i (consecutive n2)
+    const float2* tws = pl.s2.tw + pl.s2.tws_off[0];
+    const int items = m0 * nrows;
+    for (int id = threadIdx.x; id < items; id += kThreads) {
+      const int c = id / m0, i = id - c * m0;
+      const float2* p = tile + i * WP + c;
+      float2 v[R0];
+#pragma unroll
+      for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
+      const float2* w = tws + i * (R0 - 1);
+#pragma unroll
+      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+      inv_dft<R0>(v);
+      const int g = (row0 + c) * N2 + i;
+#pragma unroll
+      for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&pl.twm[g + q * m0]));
+    }
+  } else {
+    inv_stage_smem<S, 0, WP>(tile, nrows, pl.s2.tw, pl.s2.tws_off[0]);
+    for (int c = tb; c < nrows; c += nb)
+      for (int e = tc; e < N2; e += kTW) {
+        const int g = (row0 + c) * N2 + e;
+        out[g] = cmulc(tile[e * WP + c], __ldg(&pl.twm[g]));
+      }
+  }
+}
+
+// =========================================================================== cols kernel
+// grid = (ceil(N2/16), units), as k_corr_cols. S = schedule of the length-N1 transform.
+template <class S>
+__global__ void __launch_bounds__(kThreads, 2)
+k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int D, int d0, int u0,
+              int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
+  GNSSACQ_DYN_SMEM(float2, tile);
+  constexpr int N1 = S::F, WP = kTileW, NS = S::NS;
+  const int N = pl.N, N2 = pl.N2;
+  float* qs = reinterpret_cast<float*>(tile + N1 * WP);
+  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
+  constexpr int nb = kThreads / kTW;
+  const int col0 = blockIdx.x * kTileW;
+  const int ncols = imin(kTileW, N2 - col0);
+  const int ul = blockIdx.y, u = u0 + ul;
+  const int r = u % R_, dd = u / R_;
+  unsigned long long key = 0ull;
+  float sum = 0.f;
+  float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
+
+  for (int b = 0; b < B; ++b) {
+    const float2* in = scratch + ((long long)ul * B + b) * N + col0 + tc;
+    const bool last = (b + 1 == B);
+    // ---- first inverse stage fused with the coalesced load
+    {
+      constexpr int R = S::radix(NS - 1), nbf = N1 / R;
+      if (tc < ncols) {
+#pragma unroll 2
+        for (int bf = tb; bf < nbf; bf += nb) {
+          float2 v[R];
+#pragma unroll
+          for (int q = 0; q < R; ++q) v[q] = in[(bf * R + q) * N2];
+          inv_dft<R>(v);
+#pragma unroll
+          for (int q = 0; q < R; ++q) tile[(bf * R + q) * WP + tc] = v[q];
+        }
+      }
+      __syncthreads();
+    }
+    inv_stages_smem<S, NS - 2, 1, WP>(tile, ncols, pl.s1);
+    // ---- last inverse stage fused with |.|, the non-coherent sum and the peak search
+    constexpr int R0 = S::radix(0), m0 = S::stride(0);
+    auto sink = [&](int n1, float2 v) {
+      const int lag = n1 * N2 + col0 + tc;
+      float acc = __fsqrt_rn(v.x * v.x + v.y * v.y) * scale;
+      if (b > 0) acc += qs[n1 * WP + tc];
+      if (!last) { qs[n1 * WP + tc] = acc; }
+      else {
+        sum += acc;
+        if (lag < n_lags) { const unsigned long long k = pack_key(acc, lag); key = k > key ? k : key; }
+        if (qd) qd[lag] = acc;
+      }
+    };
+    if constexpr (is_split_radix(R0)) {
+      // warp-pair butterfly (see stage_tile_split): both warps load, each emits half the outputs
+      constexpr int H = (R0 - 1) / 2, KA = (H + 1) / 2;
+      const int warp = threadIdx.x >> 5, role = warp & 1;
+      const int slot = (warp >> 1) * 2 + ((threadIdx.x >> 4) & 1);
+      constexpr int nslots = kThreads >> 5;
+      const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+      for (int i = slot; i < m0; i += nslots) {
+        if (tc < ncols) {
+          const float2* p = tile + i * WP + tc;
+          const float2* w = tws + i * (R0 - 1);
+          float2 a[H + 1], bq[H + 1];
+          const float2 x0 = cswap(p[0]);
+          static_for<1, H + 1>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
+            const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
+            a[j] = cadd(s, t);
+            bq[j] = csub(s, t);
+          });
+          auto emit = [&](int q, float2 v) { sink(i + q * m0, cswap(v)); };
+          if (role == 0) {
+            float2 s0 = x0;
+            static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
+            emit(0, s0);
+            prime_outputs<R0, 1, KA>(x0, a, bq, emit);
+          } else {
+            prime_outputs<R0, KA + 1, H>(x0, a, bq, emit);
+          }
+        }
+      }
+    } else {
+      const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+      if (tc < ncols) {
+#pragma unroll 2
+        for (int i = tb; i < m0; i += nb) {
+          const float2* p = tile + i * WP + tc;
+          float2 v[R0];
+#pragma unroll
+          for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
+          const float2* w = tws + i * (R0 - 1);
+#pragma unroll
+          for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+          inv_dft<R0>(v);
+#pragma unroll
+          for (int q = 0; q < R0; ++q) sink(i + q * m0, v[q]);
+        }
+      }
+    }
+    if (!last) __syncthreads();       // tile and q are reused by the next block
+  }
+  block_reduce_part(key, sum);
+  if (threadIdx.x == 0) {
+    Part p; p.key = key; p.sum = sum; p.pad = 0.f;
+    parts[((long long)r * D + d0 + dd) * ntiles + blockIdx.x] = p;
+  }
+}
+
+// --------------------------------------------------------------------------- registry
+// Schedules exactly as fft_plan.h::make_subplan emits them (odd primes descending, then
+// powers of two as 16/8/4/2): checked against the runtime plan before use.
+using S128 = Sub<128, 16, 8>;
+using S256 = Sub<256, 16, 16>;
+using S512 = Sub<512, 8, 8, 8>;
+using S320 = Sub<320, 5, 8, 8>;
+using S165 = Sub<165, 11, 5, 3>;
+using S186 = Sub<186, 31, 3, 2>;
+using S220 = Sub<220, 11, 5, 4>;
+using S279 = Sub<279, 31, 3, 3>;
+using S372 = Sub<372, 31, 3, 4>;
+using S440 = Sub<440, 11, 5, 8>;
+using S200 = Sub<200, 5, 5, 8>;
+using S250 = Sub<250, 5, 5, 5, 2>;
+
+typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
+typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
+
+template <class S> inline bool schedule_matches(const SubPlan& sp) {
+  if (sp.F != S::F || sp.ns != S::NS) return false;
+  for (int j = 0; j < S::NS; ++j)
+    if (sp.radix[j] != S::radix(j) || sp.m[j] != S::stride(j)) return false;
+  return true;
+}
+
+inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
+#define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
+  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250)
+#undef GNSSACQ_TRY
+  return nullptr;
+}
+inline corr_cols_fn find_cols_kernel(const SubPlan& s1) {
+#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return k_corr_cols_s<S>;
+  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
+  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200)
+#undef GNSSACQ_TRY
+  return nullptr;
+}
+
+}  // namespace acq

@@ -37,12 +37,14 @@ def _declare(lib):
         'gnssacq_set_replicas': [p, p, i32, i32],
         'gnssacq_set_replicas_device': [p, p, i32, i32],
         'gnssacq_set_profiling': [p, i32],
+        'gnssacq_set_option': [p, C.c_char_p, i32],
         'gnssacq_get_stage_times': [p, p, p, i32],
         'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
         'gnssacq_mix': [p, p, i64, dbl, dbl],
         'gnssacq_plan_info': [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         'gnssacq_synchronize': [p],
+        'gnssacq_kernel_variant': [p],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -128,6 +130,9 @@ class Engine:
         self._check(self._lib.gnssacq_set_replicas_device(self._h, C.c_void_p(int(device_ptr)), int(R), int(N)))
         self.R, self.N = int(R), int(N)
 
+    def set_option(self, name, value):
+        self._check(self._lib.gnssacq_set_option(self._h, name.encode(), int(value)))
+
     def set_profiling(self, on):
         self._check(self._lib.gnssacq_set_profiling(self._h, int(bool(on))))
 
@@ -167,6 +172,12 @@ class Engine:
         v = [C.c_int32() for _ in range(4)]
         self._check(self._lib.gnssacq_plan_info(self._h, *[C.byref(a) for a in v]))
         return dict(N=v[0].value, N1=v[1].value, N2=v[2].value, large=bool(v[3].value))
+
+    def kernel_variant(self):
+        v = self._lib.gnssacq_kernel_variant(self._h)
+        if v < 0:
+            self._check(v)
+        return v
 
     def launch_count(self):
         return int(self._lib.gnssacq_launch_count(self._h))

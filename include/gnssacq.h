@@ -101,7 +101,14 @@ int gnssacq_mix(gnssacq_t* h, float* iq_c64, int64_t n_samples, double f, double
 /* Introspection for tests and the benchmark. */
 int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
+/* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =
+ * specialised columns kernel; 0 = generic runtime-planned kernels. Negative on error. */
+int gnssacq_kernel_variant(gnssacq_t* h);
 int gnssacq_synchronize(gnssacq_t* h);
+/* Tuning switches, for tests and A/B measurements. "specialized_kernels" (default 1): use the
+ * plan-specialised correlate kernels when the FFT length has one; 0 forces the generic
+ * runtime-planned kernels. Both produce the same results to rounding. */
+int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Per-stage device time: when profiling is on, CUDA events bracket the launches of each stage
  * on the handle's stream. Stages: 0 wipe-off+forward FFT, 1 correlate rows kernel (large
  * plans only), 2 correlate kernel (mid plans) / correlate columns kernel (large plans),
