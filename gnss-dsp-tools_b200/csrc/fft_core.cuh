@@ -30,6 +30,7 @@ struct SubPlan {
                             // per-stage tables below
   int tws_off[kMaxStages];  // stage j twiddles, butterfly-major: tw[tws_off[j] + i*(R-1) + (q-1)]
                             //   = exp(-2*pi*i * q*i / (R*m)),  i < m, 1 <= q < R   (0 if m == 1)
+  int tws0_t_off;           // stage 0 again, q-major: tw[tws0_t_off + (q-1)*m + i]
 };
 
 // ---------------------------------------------------------------- complex helpers
@@ -275,9 +276,10 @@ __device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, 
   });
 }
 
-template <int P, bool INV>
-__device__ __forceinline__ void stage_tile_split(float2* tile, int WP, int ncols, int F, int m,
-                                                 const float2* __restrict__ tw) {
+template <int P, bool INV, int ES = 0, int CS = 1>
+__device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F, int m,
+                                                 const float2* __restrict__ tw, int WPrt = 0) {
+  const int WP = ES ? ES : WPrt;             // element stride: compile-time when ES != 0
   constexpr int H = (P - 1) / 2;
   constexpr int KA = (H + 1) / 2;            // even warp: k = 1..KA (+ output 0); odd warp: KA+1..H
   const int tc = threadIdx.x & (kTW - 1);
@@ -295,7 +297,7 @@ __device__ __forceinline__ void stage_tile_split(float2* tile, int WP, int ncols
     const bool active = bf < nbf && c0 + tc < ncols;
     const int blk = bf / m;
     const int i = bf - blk * m;
-    float2* p = tile + (blk * P * m + i) * WP + c0 + tc;
+    float2* p = tile + (blk * P * m + i) * WP + (c0 + tc) * CS;
     const int twi = i * twstep;
     float2 a[H + 1], b[H + 1];
     float2 x0 = make_float2(0.f, 0.f);
@@ -364,7 +366,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float2* tile, int WP, int 
                 case 7: stage_tile<7, INV>(tile, WP, ncols, F, m, tw); break;
                 case 11: stage_tile<11, INV>(tile, WP, ncols, F, m, tw); break;
                 case 13: stage_tile<13, INV>(tile, WP, ncols, F, m, tw); break;
-                case 31: stage_tile_split<31, INV>(tile, WP, ncols, F, m, tw); break;
+                case 31: stage_tile_split<31, INV>(tile, ncols, F, m, tw, WP); break;
                 default: break;   // the host planner never emits other radices
               }
             }

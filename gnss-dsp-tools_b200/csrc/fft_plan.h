@@ -16,6 +16,7 @@ struct HostSubPlan {
   int F = 0;
   std::vector<int> radix, m;
   std::vector<int> tws_off;          // offset of each stage's butterfly-major twiddle table
+  int tws0_t_off = 0;                // offset of stage 0's q-major copy
   std::vector<int> pos_of_freq;      // position of frequency k after the forward transform
   std::vector<int> freq_of_pos;
 };
@@ -89,6 +90,15 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
     sp.tws_off[j] = (int)t.size();
     for (int i = 0; i < m; ++i)
       for (int q = 1; q < R; ++q) {
+        double a = -2.0 * M_PI * (double)((long long)q * i) / (double)(R * m);
+        t.push_back(make_float2((float)cos(a), (float)sin(a)));
+      }
+  }
+  if (!sp.radix.empty() && sp.m[0] > 1) {
+    const int R = sp.radix[0], m = sp.m[0];
+    sp.tws0_t_off = (int)t.size();
+    for (int q = 1; q < R; ++q)
+      for (int i = 0; i < m; ++i) {
         double a = -2.0 * M_PI * (double)((long long)q * i) / (double)(R * m);
         t.push_back(make_float2((float)cos(a), (float)sin(a)));
       }

@@ -101,6 +101,7 @@ void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
     sp.m[j] = j < sp.ns ? hs.m[j] : 1;
     sp.tws_off[j] = j < sp.ns ? hs.tws_off[j] : 0;
   }
+  sp.tws0_t_off = hs.tws0_t_off;
   sp.tw = tw;
 }
 
@@ -219,7 +220,7 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
     } else {
       const size_t smr = rows_smem(p), smc = cols_smem(p, B > 1);
       corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2) : nullptr;
-      corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1) : nullptr;
+      corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1, B > 1) : nullptr;
       if (!kr) kr = k_corr_rows<RC>;
       if (!kc) kc = k_corr_cols<RC>;
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
@@ -491,7 +492,7 @@ int64_t gnssacq_launch_count(gnssacq_t* h) { return h ? h->launches : 0; }
 int gnssacq_kernel_variant(gnssacq_t* h) {
   if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
   if (!h->hp.large || !h->use_spec) return 0;
-  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1) ? 2 : 0);
+  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

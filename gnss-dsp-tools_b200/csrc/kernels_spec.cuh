@@ -40,13 +40,15 @@ template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
   for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
 }
 
-// ---- one in-shared-memory inverse stage (stage J of S), tile pitch WP, ncols live columns
-template <class S, int J, int WP>
+// ---- one in-shared-memory inverse stage (stage J of S). Element e of column c lives at
+// tile[e*ES + c*CS]: the columns kernel uses (ES, CS) = (16, 1), the rows kernel (1, odd pitch)
+// — either way the 16 lanes of a half-warp (consecutive c) hit 16 distinct bank pairs.
+template <class S, int J, int ES, int CS>
 __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const float2* __restrict__ twbase, int twoff) {
   constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
   const int tc = threadIdx.x & (kTW - 1);
   if constexpr (is_split_radix(R)) {
-    stage_tile_split<R, true>(tile, WP, ncols, S::F, m, twbase);      // warp-pair version, W_F table
+    stage_tile_split<R, true, ES, CS>(tile, ncols, S::F, m, twbase);   // warp-pair version, W_F table
   } else {
     const int tb = threadIdx.x / kTW;
     constexpr int nb = kThreads / kTW;
@@ -55,10 +57,10 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
 #pragma unroll 2
       for (int bf = tb; bf < nbf; bf += nb) {
         const int blk = bf / m, i = bf - blk * m;
-        float2* p = tile + (blk * R * m + i) * WP + tc;
+        float2* p = tile + (blk * R * m + i) * ES + tc * CS;
         float2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = p[q * m * WP];
+        for (int q = 0; q < R; ++q) v[q] = p[q * m * ES];
         if constexpr (m > 1) {
           const float2* w = tws + i * (R - 1);
 #pragma unroll
@@ -66,29 +68,36 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
         }
         inv_dft<R>(v);
 #pragma unroll
-        for (int q = 0; q < R; ++q) p[q * m * WP] = v[q];
+        for (int q = 0; q < R; ++q) p[q * m * ES] = v[q];
       }
     }
   }
   __syncthreads();
 }
 
-template <class S, int J, int JEND, int WP>
+template <class S, int J, int JEND, int ES, int CS>
 __device__ __forceinline__ void inv_stages_smem(float2* tile, int ncols, const SubPlan& sp) {
   if constexpr (J >= JEND) {
-    inv_stage_smem<S, J, WP>(tile, ncols, sp.tw, sp.tws_off[J]);
-    inv_stages_smem<S, J - 1, JEND, WP>(tile, ncols, sp);
+    inv_stage_smem<S, J, ES, CS>(tile, ncols, sp.tw, sp.tws_off[J]);
+    inv_stages_smem<S, J - 1, JEND, ES, CS>(tile, ncols, sp);
   }
 }
 
 // =========================================================================== rows kernel
 // grid = (ceil(N1/16), B, units), as k_corr_rows. S = schedule of the length-N2 transform.
+// The tile is row-major like memory, tile[c*P + e] with an odd pitch P, so the global loads
+// and stores are straight coalesced row copies and no transposition is needed.
+template <class S> __host__ __device__ constexpr int rows_pitch() { return S::F | 1; }
+template <class S> __host__ __device__ constexpr size_t rows_spec_smem() { return (size_t)kTileW * rows_pitch<S>() * sizeof(float2); }
+
+template <class S> __host__ __device__ constexpr int rows_min_ctas() { return rows_spec_smem<S>() * 3 <= 200 * 1024 ? 3 : 2; }
+
 template <class S>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, rows_min_ctas<S>())
 k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
               int R_, int B, int u0, float2* __restrict__ scratch) {
   GNSSACQ_DYN_SMEM(float2, tile);
-  constexpr int N2 = S::F, WP = kRowPitch, NS = S::NS;
+  constexpr int N2 = S::F, P = rows_pitch<S>(), NS = S::NS;
   const int N = pl.N, N1 = pl.N1;
   const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
   constexpr int nb = kThreads / kTW;
@@ -96,63 +105,66 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
   const int nrows = imin(kTileW, N1 - row0);
   const int b = blockIdx.y, ul = blockIdx.z, u = u0 + ul;
   const int r = u % R_, dd = u / R_;
-  const float2* Cr = C + (long long)r * N;
-  const float2* Xb = X + ((long long)dd * B + b) * N;
+  const float2* Cr = C + (long long)r * N + (long long)row0 * N2;
+  const float2* Xb = X + ((long long)dd * B + b) * N + (long long)row0 * N2;
 
-  // ---- first inverse stage (last forward stage, unit stride) fused with load + multiply
-  {
-    constexpr int R = S::radix(NS - 1), nbf = N2 / R;
-    if (tc < nrows) {
-      const int rowoff = (row0 + tc) * N2;
-#pragma unroll 2
-      for (int bf = tb; bf < nbf; bf += nb) {
-        const int g = rowoff + bf * R;
-        float2 v[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = cmulc(__ldg(&Cr[g + q]), __ldg(&Xb[g + q]));
-        inv_dft<R>(v);
-#pragma unroll
-        for (int q = 0; q < R; ++q) tile[(bf * R + q) * WP + tc] = v[q];
-      }
-    }
-    __syncthreads();
+  // ---- coalesced load of the 16 rows, multiplied by the replica spectrum on the way in
+  for (int c = tb; c < nrows; c += nb) {
+    const float2* xr = Xb + c * N2;
+    const float2* cr = Cr + c * N2;
+    float2* trow = tile + c * P;
+#pragma unroll 8
+    for (int e = tc; e < N2; e += kTW) trow[e] = cmulc(__ldg(&cr[e]), __ldg(&xr[e]));
   }
-  // ---- middle stages in shared memory
-  inv_stages_smem<S, NS - 2, 1, WP>(tile, nrows, pl.s2);
+  __syncthreads();
+  // ---- inverse stages NS-1 .. 1 in shared memory
+  inv_stages_smem<S, NS - 1, 1, 1, P>(tile, nrows, pl.s2);
   // ---- last inverse stage (first forward stage, stride m0)
-  float2* out = scratch + ((long long)ul * B + b) * N;
+  float2* out = scratch + ((long long)ul * B + b) * N + (long long)row0 * N2;
+  const float2* twm = pl.twm + (long long)row0 * N2;
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
   if constexpr (!is_split_radix(R0) && m0 >= 16) {
-    // fused with the conjugate four-step twiddle and the store: lanes walk i (consecutive n2)
-    const float2* tws = pl.s2.tw + pl.s2.tws_off[0];
+    // fused with the conjugate four-step twiddle and the store: lanes walk i (consecutive n2),
+    // stage twiddles come from the transposed table (q-major) so lanes read them contiguously
+    const float2* twt = pl.s2.tw + pl.s2.tws0_t_off;
     const int items = m0 * nrows;
     for (int id = threadIdx.x; id < items; id += kThreads) {
       const int c = id / m0, i = id - c * m0;
-      const float2* p = tile + i * WP + c;
+      const float2* p = tile + c * P + i;
       float2 v[R0];
 #pragma unroll
-      for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
-      const float2* w = tws + i * (R0 - 1);
+      for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
 #pragma unroll
-      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
       inv_dft<R0>(v);
-      const int g = (row0 + c) * N2 + i;
+      const int g = c * N2 + i;
 #pragma unroll
-      for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&pl.twm[g + q * m0]));
+      for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
     }
   } else {
-    inv_stage_smem<S, 0, WP>(tile, nrows, pl.s2.tw, pl.s2.tws_off[0]);
+    inv_stage_smem<S, 0, 1, P>(tile, nrows, pl.s2.tw, pl.s2.tws_off[0]);
     for (int c = tb; c < nrows; c += nb)
       for (int e = tc; e < N2; e += kTW) {
-        const int g = (row0 + c) * N2 + e;
-        out[g] = cmulc(tile[e * WP + c], __ldg(&pl.twm[g]));
+        const int g = c * N2 + e;
+        out[g] = cmulc(tile[c * P + e], __ldg(&twm[g]));
       }
   }
 }
 
 // =========================================================================== cols kernel
 // grid = (ceil(N2/16), units), as k_corr_cols. S = schedule of the length-N1 transform.
-template <class S>
+// MULTI = more than one non-coherent block (q kept in shared memory between blocks).
+__device__ __forceinline__ float sqrt_fast(float a) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));     // MUFU.SQRT, <= 1 ulp: far inside the 1e-4 budget
+  return r;
+#else
+  return sqrtf(a);
+#endif
+}
+
+template <class S, bool MULTI>
 __global__ void __launch_bounds__(kThreads, 2)
 k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int D, int d0, int u0,
               int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
@@ -166,12 +178,15 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
   const int ncols = imin(kTileW, N2 - col0);
   const int ul = blockIdx.y, u = u0 + ul;
   const int r = u % R_, dd = u / R_;
-  unsigned long long key = 0ull;
-  float sum = 0.f;
+  // Per-thread running peak over the eligible lags (unscaled; 1/N is applied once at the end).
+  float best = -1.f, sum = 0.f;
+  int bestlag = 0x7fffffff;
   float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
+  const bool dump = qd != nullptr;
+  const int lag0 = col0 + tc;
 
   for (int b = 0; b < B; ++b) {
-    const float2* in = scratch + ((long long)ul * B + b) * N + col0 + tc;
+    const float2* in = scratch + ((long long)ul * B + b) * N + lag0;
     const bool last = (b + 1 == B);
     // ---- first inverse stage fused with the coalesced load
     {
@@ -189,19 +204,21 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
       }
       __syncthreads();
     }
-    inv_stages_smem<S, NS - 2, 1, WP>(tile, ncols, pl.s1);
+    inv_stages_smem<S, NS - 2, 1, WP, 1>(tile, ncols, pl.s1);
     // ---- last inverse stage fused with |.|, the non-coherent sum and the peak search
     constexpr int R0 = S::radix(0), m0 = S::stride(0);
     auto sink = [&](int n1, float2 v) {
-      const int lag = n1 * N2 + col0 + tc;
-      float acc = __fsqrt_rn(v.x * v.x + v.y * v.y) * scale;
-      if (b > 0) acc += qs[n1 * WP + tc];
-      if (!last) { qs[n1 * WP + tc] = acc; }
-      else {
-        sum += acc;
-        if (lag < n_lags) { const unsigned long long k = pack_key(acc, lag); key = k > key ? k : key; }
-        if (qd) qd[lag] = acc;
+      float acc = sqrt_fast(v.x * v.x + v.y * v.y);
+      if (MULTI) {
+        if (b > 0) acc += qs[n1 * WP + tc];
+        if (!last) { qs[n1 * WP + tc] = acc; return; }
       }
+      sum += acc;
+      if (acc >= best) {                       // rare after the first few samples
+        const int lag = n1 * N2 + lag0;
+        if (lag < n_lags && (acc > best || lag < bestlag)) { best = acc; bestlag = lag; }
+      }
+      if (dump) qd[n1 * N2 + lag0] = acc * scale;
     };
     if constexpr (is_split_radix(R0)) {
       // warp-pair butterfly (see stage_tile_split): both warps load, each emits half the outputs
@@ -223,7 +240,7 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
             a[j] = cadd(s, t);
             bq[j] = csub(s, t);
           });
-          auto emit = [&](int q, float2 v) { sink(i + q * m0, cswap(v)); };
+          auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };      // |.| ignores the re/im swap
           if (role == 0) {
             float2 s0 = x0;
             static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
@@ -246,14 +263,18 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
           const float2* w = tws + i * (R0 - 1);
 #pragma unroll
           for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
-          inv_dft<R0>(v);
+#pragma unroll
+          for (int q = 0; q < R0; ++q) v[q] = cswap(v[q]);
+          Dft<R0>::run(v);                                                 // |.| ignores the swap back
 #pragma unroll
           for (int q = 0; q < R0; ++q) sink(i + q * m0, v[q]);
         }
       }
     }
-    if (!last) __syncthreads();       // tile and q are reused by the next block
+    if (MULTI && !last) __syncthreads();       // tile and q are reused by the next block
   }
+  unsigned long long key = bestlag != 0x7fffffff ? pack_key(best * scale, bestlag) : 0ull;
+  sum *= scale;
   block_reduce_part(key, sum);
   if (threadIdx.x == 0) {
     Part p; p.key = key; p.sum = sum; p.pad = 0.f;
@@ -294,8 +315,8 @@ inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
 #undef GNSSACQ_TRY
   return nullptr;
 }
-inline corr_cols_fn find_cols_kernel(const SubPlan& s1) {
-#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return k_corr_cols_s<S>;
+inline corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi) {
+#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return multi ? k_corr_cols_s<S, true> : k_corr_cols_s<S, false>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
   GNSSACQ_TRY(S372) GNSSACQ_TRY(S200)
 #undef GNSSACQ_TRY
