@@ -163,6 +163,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--opt', action='append', default=[], help='engine option name=value (A/B measurements)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
     if args.impl == 'reference':
@@ -196,6 +197,9 @@ def main():
     assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.set_profiling(True)
+    for kv in args.opt:
+        k, v = kv.split('=')
+        eng.set_option(k, int(v))
 
     # ---- device-resident inputs for `value`
     x_dev = torch.from_numpy(x.view(np.float32).copy()).to(dev)

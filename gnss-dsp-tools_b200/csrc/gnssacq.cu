@@ -27,7 +27,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // Working-set budgets: keep the per-chunk capture spectra and the inverse-FFT scratch
 // L2-resident (B200 L2 is ~126 MB) so the correlate kernels re-read them from L2, not HBM.
 constexpr size_t kXChunkBytes = 48u << 20;
-constexpr size_t kScratchBytes = 40u << 20;
+constexpr size_t kScratchBytes = 40u << 20;     // split over the two lanes when chunks overlap
 
 struct DevBuf {
   void* p = nullptr;
@@ -71,6 +71,11 @@ struct gnssacq {
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
+  bool overlap = true;                // large plans: alternate unit chunks over two streams so the
+                                      // rows kernel of one chunk overlaps the columns kernel of the other
+  cudaStream_t lane[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  DevBuf d_scratch2;
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -226,18 +231,43 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
       if (int rc2 = allow_smem(h, kc, smc)) return rc2;
       const int units = R * dc;
-      for (int u0 = 0; u0 < units; u0 += Uc) {
-        const int uc = std::min(Uc, units - u0);
-        {
-          StageTimer timer(h, kStageCorrRows, 1);
-          GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, h->stream,
-                         p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
+      const bool two_lanes = h->overlap && units > Uc;
+      if (two_lanes) {
+        // fork: both lanes wait for everything queued so far on the main stream (the forward FFTs)
+        StageTimer timer(h, kStageCorrCols, 0);        // whole correlate section, as seen by the main stream
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        for (int l = 0; l < 2; ++l) CU(cudaStreamWaitEvent(h->lane[l], h->ev_fork, 0));
+        int k = 0, nl = 0;
+        for (int u0 = 0; u0 < units; u0 += Uc, ++k) {
+          const int uc = std::min(Uc, units - u0);
+          cudaStream_t st = h->lane[k & 1];
+          float2* scr = (k & 1) ? h->d_scratch2.as<float2>() : h->d_scratch.as<float2>();
+          GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, st,
+                         p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, scr);
+          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
+                         ntiles, h->d_parts.as<Part>(), d_qdump);
+          nl += 2;
         }
-        StageTimer timer(h, kStageCorrCols, 1);
-        GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, h->stream, p,
-                       h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
-                       h->d_parts.as<Part>(), d_qdump);
-        h->launches += 2;
+        h->launches += nl;
+        h->prof_launches[kStageCorrCols] += h->profiling ? nl : 0;
+        for (int l = 0; l < 2; ++l) {                  // join
+          CU(cudaEventRecord(h->ev_join[l], h->lane[l]));
+          CU(cudaStreamWaitEvent(h->stream, h->ev_join[l], 0));
+        }
+      } else {
+        for (int u0 = 0; u0 < units; u0 += Uc) {
+          const int uc = std::min(Uc, units - u0);
+          {
+            StageTimer timer(h, kStageCorrRows, 1);
+            GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, h->stream,
+                           p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
+          }
+          StageTimer timer(h, kStageCorrCols, 1);
+          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, h->stream, p,
+                         h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
+                         h->d_parts.as<Part>(), d_qdump);
+          h->launches += 2;
+        }
       }
     }
     CU(cudaGetLastError());
@@ -271,9 +301,12 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
   int Uc = 0;
   if (large) {
-    Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, kScratchBytes / (tbytes * B)));
+    const size_t budget = h->overlap ? kScratchBytes / 2 : kScratchBytes;
+    Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, budget / (tbytes * B)));
     Uc = std::min(Uc, 65535);
     if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
+    if (h->overlap && R * Dc > Uc)
+      if (int rc = h->d_scratch2.ensure((size_t)Uc * B * tbytes)) return rc;
   }
   for (int d0 = 0; d0 < D; d0 += Dc) {
     const int dc = std::min(Dc, D - d0);
@@ -309,6 +342,11 @@ int gnssacq_create(int device, gnssacq_t** out) {
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  for (int l = 0; l < 2 && e == cudaSuccess; ++l) {
+    e = cudaStreamCreateWithFlags(&h->lane[l], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(GNSSACQ_ECUDA, cudaGetErrorString(e)); }
   h->smem_optin = prop.sharedMemPerBlockOptin;
   h->stream = h->own_stream;
@@ -332,6 +370,12 @@ int gnssacq_destroy(gnssacq_t* h) {
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  for (int l = 0; l < 2; ++l) {
+    if (h->lane[l]) { cudaStreamSynchronize(h->lane[l]); cudaStreamDestroy(h->lane[l]); }
+    if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  h->d_scratch2.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -399,6 +443,7 @@ int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
+  if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
   return fail(GNSSACQ_EINVAL, std::string("unknown option ") + name);
 }
 

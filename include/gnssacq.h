@@ -107,7 +107,10 @@ int gnssacq_kernel_variant(gnssacq_t* h);
 int gnssacq_synchronize(gnssacq_t* h);
 /* Tuning switches, for tests and A/B measurements. "specialized_kernels" (default 1): use the
  * plan-specialised correlate kernels when the FFT length has one; 0 forces the generic
- * runtime-planned kernels. Both produce the same results to rounding. */
+ * runtime-planned kernels. Both produce the same results to rounding.
+ * "overlap_chunks" (default 1): large plans alternate their unit chunks over two internal
+ * streams so the rows kernel of one chunk overlaps the columns kernel of the other; 0 runs
+ * every kernel back to back on the handle's stream (what per-kernel stage times need). */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Per-stage device time: when profiling is on, CUDA events bracket the launches of each stage
  * on the handle's stream. Stages: 0 wipe-off+forward FFT, 1 correlate rows kernel (large

@@ -110,6 +110,9 @@ static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(1); return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = malloc(1); return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return 0; }
 struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; int l2CacheSize; char name[64]; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
