@@ -24,9 +24,11 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(GNSSACQ_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
-// Working-set budgets: keep the per-chunk capture spectra and the inverse-FFT scratch
-// L2-resident (B200 L2 is ~126 MB) so the correlate kernels re-read them from L2, not HBM.
-constexpr size_t kXChunkBytes = 48u << 20;
+// Working-set budgets. Units are ordered replica-fastest, so a Doppler bin's spectra X[d] are
+// re-read by R consecutive units and then never again: the capture-spectra chunk may be large
+// (memory-bound only). What must stay L2-resident (B200 L2 ~126 MB) is the replica spectra C
+// plus the inverse-FFT scratch between the rows and columns kernels.
+constexpr size_t kXChunkBytes = 512u << 20;
 constexpr size_t kScratchBytes = 40u << 20;     // split over the two lanes when chunks overlap
 
 struct DevBuf {
@@ -73,9 +75,13 @@ struct gnssacq {
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
   bool overlap = true;                // large plans: alternate unit chunks over two streams so the
                                       // rows kernel of one chunk overlaps the columns kernel of the other
-  cudaStream_t lane[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-  DevBuf d_scratch2;
+  static constexpr int kMaxLanes = 4;
+  int nlanes = 2;
+  size_t scratch_bytes = kScratchBytes;   // total over all lanes
+  size_t xchunk_bytes = kXChunkBytes;
+  cudaStream_t lane[kMaxLanes] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
+  DevBuf d_scratch_lane[kMaxLanes];
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -236,12 +242,12 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
         // fork: both lanes wait for everything queued so far on the main stream (the forward FFTs)
         StageTimer timer(h, kStageCorrCols, 0);        // whole correlate section, as seen by the main stream
         CU(cudaEventRecord(h->ev_fork, h->stream));
-        for (int l = 0; l < 2; ++l) CU(cudaStreamWaitEvent(h->lane[l], h->ev_fork, 0));
+        for (int l = 0; l < h->nlanes; ++l) CU(cudaStreamWaitEvent(h->lane[l], h->ev_fork, 0));
         int k = 0, nl = 0;
         for (int u0 = 0; u0 < units; u0 += Uc, ++k) {
           const int uc = std::min(Uc, units - u0);
-          cudaStream_t st = h->lane[k & 1];
-          float2* scr = (k & 1) ? h->d_scratch2.as<float2>() : h->d_scratch.as<float2>();
+          cudaStream_t st = h->lane[k % h->nlanes];
+          float2* scr = h->d_scratch_lane[k % h->nlanes].as<float2>();
           GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, st,
                          p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, scr);
           GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
@@ -250,7 +256,7 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
         }
         h->launches += nl;
         h->prof_launches[kStageCorrCols] += h->profiling ? nl : 0;
-        for (int l = 0; l < 2; ++l) {                  // join
+        for (int l = 0; l < h->nlanes; ++l) {          // join
           CU(cudaEventRecord(h->ev_join[l], h->lane[l]));
           CU(cudaStreamWaitEvent(h->stream, h->ev_join[l], 0));
         }
@@ -296,17 +302,18 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   CU(cudaMemcpyAsync(h->d_freq.p, nco_freq, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (int rc = h->d_parts.ensure((size_t)R * D * ntiles * sizeof(Part))) return rc;
 
-  int Dc = (int)std::max<size_t>(1, std::min<size_t>((size_t)D, kXChunkBytes / (tbytes * B)));
+  int Dc = (int)std::max<size_t>(1, std::min<size_t>((size_t)D, h->xchunk_bytes / (tbytes * B)));
   Dc = std::max(1, std::min(Dc, 65535 / B));
   if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
   int Uc = 0;
   if (large) {
-    const size_t budget = h->overlap ? kScratchBytes / 2 : kScratchBytes;
+    const size_t budget = h->overlap ? h->scratch_bytes / h->nlanes : h->scratch_bytes;
     Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, budget / (tbytes * B)));
     Uc = std::min(Uc, 65535);
     if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
     if (h->overlap && R * Dc > Uc)
-      if (int rc = h->d_scratch2.ensure((size_t)Uc * B * tbytes)) return rc;
+      for (int l = 0; l < h->nlanes; ++l)
+        if (int rc = h->d_scratch_lane[l].ensure((size_t)Uc * B * tbytes)) return rc;
   }
   for (int d0 = 0; d0 < D; d0 += Dc) {
     const int dc = std::min(Dc, D - d0);
@@ -342,7 +349,7 @@ int gnssacq_create(int device, gnssacq_t** out) {
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-  for (int l = 0; l < 2 && e == cudaSuccess; ++l) {
+  for (int l = 0; l < gnssacq::kMaxLanes && e == cudaSuccess; ++l) {
     e = cudaStreamCreateWithFlags(&h->lane[l], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming);
   }
@@ -370,12 +377,12 @@ int gnssacq_destroy(gnssacq_t* h) {
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
-  for (int l = 0; l < 2; ++l) {
+  for (int l = 0; l < gnssacq::kMaxLanes; ++l) {
     if (h->lane[l]) { cudaStreamSynchronize(h->lane[l]); cudaStreamDestroy(h->lane[l]); }
     if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
+    h->d_scratch_lane[l].release();
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  h->d_scratch2.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -444,6 +451,12 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
+  if (std::string(name) == "lanes") {
+    if (value < 1 || value > gnssacq::kMaxLanes) return fail(GNSSACQ_EINVAL, "lanes must be 1..4");
+    h->nlanes = value; h->overlap = value > 1; return 0;
+  }
+  if (std::string(name) == "scratch_mb") { if (value < 1) return fail(GNSSACQ_EINVAL, "scratch_mb"); h->scratch_bytes = (size_t)value << 20; return 0; }
+  if (std::string(name) == "xchunk_mb") { if (value < 1) return fail(GNSSACQ_EINVAL, "xchunk_mb"); h->xchunk_bytes = (size_t)value << 20; return 0; }
   return fail(GNSSACQ_EINVAL, std::string("unknown option ") + name);
 }
 
