@@ -54,6 +54,7 @@ struct gnssacq {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int64_t launches = 0;
   size_t smem_optin = 0;
+  int num_sms = 148;
 
   std::vector<double> nco_c128;       // 1024 x (re, im)
   DevBuf d_nco_f32, d_nco_f64;
@@ -307,8 +308,16 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
   int Uc = 0;
   if (large) {
+    // Units per launch: enough to keep the scratch L2-resident when that still fills the GPU,
+    // but never fewer than two waves of columns-kernel CTAs (ntiles x units) — with many
+    // non-coherent blocks one unit's scratch alone exceeds L2, and spilling it to HBM
+    // (16 B per cell-block) costs far less than an under-filled grid.
     const size_t budget = h->overlap ? h->scratch_bytes / h->nlanes : h->scratch_bytes;
-    Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, budget / (tbytes * B)));
+    const size_t unit_bytes = tbytes * B;
+    const size_t fill = (size_t)(4 * h->num_sms + ntiles - 1) / ntiles;
+    size_t uc = std::max(budget / unit_bytes, fill);
+    uc = std::min(uc, std::max<size_t>(1, ((size_t)3 << 30) / unit_bytes));      // hard cap 3 GiB per lane
+    Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, uc));
     Uc = std::min(Uc, 65535);
     if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
     if (h->overlap && R * Dc > Uc)
@@ -356,6 +365,7 @@ int gnssacq_create(int device, gnssacq_t** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(GNSSACQ_ECUDA, cudaGetErrorString(e)); }
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   h->stream = h->own_stream;
   h->nco_c128.resize(2 * kNcoSize);
   for (int k = 0; k < kNcoSize; ++k) {
