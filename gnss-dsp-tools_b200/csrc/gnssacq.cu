@@ -2,6 +2,7 @@
 #include "../../include/gnssacq.h"
 #include "fft_plan.h"
 #include "kernels_spec.cuh"
+#include "preprocess.cuh"
 
 #include <algorithm>
 #include <new>
@@ -70,6 +71,7 @@ struct gnssacq {
   int R = 0, N = 0;
 
   DevBuf d_X, d_scratch, d_parts, d_freq, d_rec, d_q, d_tmp;
+  DevBuf d_raw, d_ext, d_y1, d_z, d_fir, d_pre128;        // capture front end
 
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
@@ -383,7 +385,8 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_C, &h->d_X,
-                    &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp})
+                    &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -543,6 +546,50 @@ int gnssacq_mix(gnssacq_t* h, float* iq, int64_t n, double f, double p) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(iq, h->d_tmp.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq, int64_t n, double mix_f, double mix_p,
+                       const double* fir, int32_t ntaps, double step, int64_t n_out, double* out_c128) {
+  if (!h || !iq || !fir || n <= 0 || ntaps <= 0 || n_out <= 0) return fail(GNSSACQ_EINVAL, "bad preprocess arguments");
+  const int edge = 3 * ntaps;                              // filtfilt default padlen = 3*max(len(a),len(b))
+  if (n <= edge) return fail(GNSSACQ_EINVAL, "recording shorter than the filter padding (filtfilt would raise)");
+  CU(cudaSetDevice(h->device));
+  const long long L = n + 2ll * edge;
+  const double scale = (double)kNcoSize * (double)(1ll << 50);
+  const long long dp0 = (long long)floor(mix_p * scale);
+  const long long df = (long long)floor(mix_f * scale);
+  if (int rc = h->d_raw.ensure((size_t)2 * n)) return rc;
+  if (int rc = h->d_ext.ensure((size_t)L * sizeof(float2))) return rc;
+  if (int rc = h->d_y1.ensure((size_t)L * sizeof(double2))) return rc;
+  if (int rc = h->d_z.ensure((size_t)L * sizeof(double2))) return rc;
+  if (int rc = h->d_fir.ensure((size_t)ntaps * sizeof(double))) return rc;
+  if (int rc = h->d_x_own.ensure((size_t)n_out * sizeof(float2))) return rc;
+  if (out_c128) if (int rc = h->d_pre128.ensure((size_t)n_out * sizeof(double2))) return rc;
+  CU(cudaMemcpyAsync(h->d_raw.p, iq, (size_t)2 * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_fir.p, fir, (size_t)ntaps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int blocks = (int)std::min<long long>((L + kThreads - 1) / kThreads, (long long)h->num_sms * 16);
+  const double2* tab = h->d_nco_f64.as<double2>();
+  GNSSACQ_LAUNCH(k_pre_extend, dim3(blocks), dim3(kThreads), 0, h->stream, h->d_raw.as<signed char>(), (long long)n, edge,
+                 (unsigned long long)dp0, (unsigned long long)df, tab, h->d_ext.as<float2>());
+  // forward pass where all taps are inside ext; backward pass over what the slice [edge, edge+n) needs
+  auto kf = k_pre_fir<1, float2>;
+  auto kb = k_pre_fir<-1, double2>;
+  GNSSACQ_LAUNCH(kf, dim3(blocks), dim3(kThreads), 0, h->stream, h->d_ext.as<float2>(), h->d_fir.as<double>(), ntaps,
+                 (long long)(ntaps - 1), L, h->d_y1.as<double2>());
+  GNSSACQ_LAUNCH(kb, dim3(blocks), dim3(kThreads), 0, h->stream, h->d_y1.as<double2>(), h->d_fir.as<double>(), ntaps,
+                 (long long)edge, (long long)edge + n, h->d_z.as<double2>());
+  const int blocks_o = (int)std::min<long long>((n_out + kThreads - 1) / kThreads, (long long)h->num_sms * 16);
+  GNSSACQ_LAUNCH(k_pre_interp, dim3(blocks_o), dim3(kThreads), 0, h->stream, h->d_z.as<double2>(), (long long)n, edge, step,
+                 (long long)n_out, h->d_x_own.as<float2>(), out_c128 ? h->d_pre128.as<double2>() : nullptr);
+  h->launches += 4;
+  CU(cudaGetLastError());
+  h->d_x = h->d_x_own.as<float2>();
+  h->n_x = n_out;
+  if (out_c128) {
+    CU(cudaMemcpyAsync(out_c128, h->d_pre128.p, (size_t)n_out * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 

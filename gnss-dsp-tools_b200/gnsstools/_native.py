@@ -42,6 +42,7 @@ def _declare(lib):
         'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
         'gnssacq_mix': [p, p, i64, dbl, dbl],
+        'gnssacq_preprocess': [p, p, i64, dbl, dbl, p, i32, dbl, i64, p],
         'gnssacq_plan_info': [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         'gnssacq_synchronize': [p],
         'gnssacq_kernel_variant': [p],
@@ -167,6 +168,20 @@ class Engine:
         if not (isinstance(x, np.ndarray) and x.dtype == np.complex64 and x.flags['C_CONTIGUOUS']):
             raise TypeError('mix needs a contiguous complex64 array (as io.get_samples_complex returns)')
         self._check(self._lib.gnssacq_mix(self._h, _ptr(x), x.size, float(f), float(p)))
+
+    def preprocess(self, raw_iq, mix_f, mix_p, fir, step, n_out, return_c128=False):
+        """int8 I/Q recording -> mix -> filtfilt(fir) -> np.interp resample, all on the device; the
+        result becomes the resident capture. raw_iq: int8 array (or bytes) of interleaved I,Q."""
+        raw = np.frombuffer(raw_iq, dtype=np.int8) if isinstance(raw_iq, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(raw_iq, dtype=np.int8)
+        if raw.size % 2:
+            raise ValueError('raw I/Q needs an even number of bytes')
+        fir = np.ascontiguousarray(fir, dtype=np.float64)
+        out = np.empty(int(n_out), np.complex128) if return_c128 else None
+        self._check(self._lib.gnssacq_preprocess(self._h, _ptr(raw), raw.size // 2, float(mix_f), float(mix_p), _ptr(fir),
+                                                 fir.size, float(step), int(n_out), _ptr(out) if return_c128 else None))
+        self.n_samples = int(n_out)
+        return out
 
     def plan_info(self):
         v = [C.c_int32() for _ in range(4)]

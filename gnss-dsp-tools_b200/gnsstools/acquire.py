@@ -131,7 +131,8 @@ def _finish(sig, L, bins, metric, lag, dbin):
 
 def acquire(signal, x, keys, doppler_search, ms, engine=None, lag_limit=0, blocks=None):
     """Search every key (PRN, or FDMA channel for GLONASS L1/L2) of `signal` in capture `x`
-    (complex, already at the script's internal rate). Returns [(metric, code_chips, doppler_hz)]
+    (complex, already at the script's internal rate; None = the capture the engine already
+    holds on the device). Returns [(metric, code_chips, doppler_hz)]
     in the order of `keys`, each equal to what the reference search() returns."""
     sig = SIGNALS[signal] if isinstance(signal, str) else signal
     eng = engine if engine is not None else _native.default_engine()
@@ -144,10 +145,15 @@ def acquire(signal, x, keys, doppler_search, ms, engine=None, lag_limit=0, block
     if B <= 0 or len(bins) == 0:
         return [_finish(sig, L, bins, 0.0, 0, -1) for _ in keys]
     need = (B - 1) * sig.n + sig.N
-    x = np.asarray(x)
-    if x.shape[0] < need:
-        raise ValueError('capture too short: %d samples, search needs %d' % (x.shape[0], need))
-    eng.set_signal(np.ascontiguousarray(x[:need], dtype=np.complex64))
+    if x is None:
+        # capture already resident on the device (acquire_cli.preprocess / Engine.preprocess)
+        if getattr(eng, 'n_samples', 0) < need:
+            raise ValueError('resident capture too short: %d samples, search needs %d' % (getattr(eng, 'n_samples', 0), need))
+    else:
+        x = np.asarray(x)
+        if x.shape[0] < need:
+            raise ValueError('capture too short: %d samples, search needs %d' % (x.shape[0], need))
+        eng.set_signal(np.ascontiguousarray(x[:need], dtype=np.complex64))
     out = []
     if sig.fdma:
         eng.set_replicas(replica(sig, None)[None, :])

@@ -21,9 +21,23 @@ from . import io, util
 from . import _native
 
 
-def preprocess(sig, x, fs, coffset, ms_pad, engine=None):
-    """Capture at the file rate -> complex128 at the script's internal rate
-    (acquire-gps-l1.py:85-96)."""
+def preprocess(sig, raw, fs, coffset, ms_pad, engine=None):
+    """Raw int8 I/Q at the file rate -> capture at the script's internal rate, resident on the
+    GPU (acquire-gps-l1.py:85-96: nco.mix, firwin/filtfilt, np.interp). Only the 161 filter
+    taps are computed on the host. Returns the number of samples produced."""
+    import scipy.signal
+    eng = engine if engine is not None else _native.default_engine()
+    per_ms = int(round(sig.fs * 0.001))
+    fsr = sig.fs / fs
+    h = scipy.signal.firwin(161, sig.cutoff / (fs / 2), window='hann')
+    n_out = ms_pad * per_ms
+    eng.preprocess(raw, -coffset / fs, 0, h, (1 / fsr), n_out)
+    return n_out
+
+
+def preprocess_host(sig, x, fs, coffset, ms_pad, engine=None):
+    """The same front end with scipy/numpy on the host, as the reference runs it (only nco.mix
+    on the GPU); kept as the cross-check for preprocess()."""
     import scipy.signal
     eng = engine if engine is not None else _native.default_engine()
     eng.mix(x, -coffset / fs, 0)                                    # nco.mix(x,-coffset/fs,0)
@@ -87,10 +101,13 @@ def main(name, argv=None, out=None, engine=None):
     ms_pad = ms + 5
     n = int(fs * 0.001 * ms_pad)
     with open(filename, "rb") as fp:
-        x = io.get_samples_complex(fp, n)
-    x = preprocess(sig, x, fs, coffset, ms_pad, engine=engine)
+        raw = fp.read(2 * n)
+    if len(raw) != 2 * n:
+        # the reference gets None from io.get_samples_complex and dies with a TypeError inside nco.mix
+        raise TypeError('short read: %s holds %d of the %d bytes needed' % (filename, len(raw), 2 * n))
+    preprocess(sig, raw, fs, coffset, ms_pad, engine=engine)
 
-    results = acq.acquire(name, x, keys, doppler_search, ms, engine=engine)
+    results = acq.acquire(name, None, keys, doppler_search, ms, engine=engine)
     for key, r in zip(keys, results):
         out.write(acq.format_result(name, key, r) + '\n')
     return results

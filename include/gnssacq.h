@@ -98,6 +98,17 @@ int gnssacq_search_device(gnssacq_t* h, const double* nco_freq, int32_t D, int32
  * buffer (copy in, mix, copy out). Bit-identical to the reference. */
 int gnssacq_mix(gnssacq_t* h, float* iq_c64, int64_t n_samples, double f, double p);
 
+/* The capture front end of every acquire-*.py (acquire-gps-l1.py:80-96) on the GPU: raw
+ * interleaved int8 I/Q (what io.get_samples_complex reads, gnsstools/io.py:3-12) ->
+ * nco.mix(x, mix_f, mix_p) -> scipy.signal.filtfilt(fir, [1], x) (default odd padding of
+ * 3*ntaps) -> np.interp at positions step*t, t < n_out. fir is the caller's firwin() result,
+ * step is the reference's (1/fsr). The complex64 result becomes the engine's capture (as if
+ * passed to gnssacq_set_signal) without leaving the device; if out_c128 is not NULL the
+ * complex128 values (equal to the scipy/numpy pipeline to ~1e-15 relative) are also copied back,
+ * interleaved re,im, n_out entries. */
+int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq_int8, int64_t n_samples, double mix_f, double mix_p,
+                       const double* fir, int32_t ntaps, double step, int64_t n_out, double* out_c128);
+
 /* Introspection for tests and the benchmark. */
 int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */

@@ -71,6 +71,7 @@ static inline double __dmul_rn(double a, double b) { volatile double r = a * b; 
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline long long __double2ll_rd(double a) { return (long long)std::floor(a); }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v) {
