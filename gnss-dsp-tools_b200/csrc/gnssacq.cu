@@ -203,8 +203,10 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
       h->launches += 1;
     } else {
       const size_t smc = cols_smem(p, false), smr = rows_smem(p);
-      auto kc = k_fwd_cols<RC, SRC>;
-      auto kr = k_fwd_rows<RC>;
+      fwd_cols_fn kc = h->use_spec ? find_fwd_cols_kernel(p.s1, SRC) : nullptr;
+      fwd_rows_fn kr = h->use_spec ? find_fwd_rows_kernel(p.s2) : nullptr;
+      if (!kc) kc = k_fwd_cols<RC, SRC>;
+      if (!kr) kr = k_fwd_rows<RC>;
       if (int rc2 = allow_smem(h, kc, smc)) return rc2;
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
       GNSSACQ_LAUNCH(kc, dim3((p.N2 + kTileW - 1) / kTileW, nt), dim3(kThreads), smc, h->stream,

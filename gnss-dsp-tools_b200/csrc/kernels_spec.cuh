@@ -164,8 +164,15 @@ __device__ __forceinline__ float sqrt_fast(float a) {
 #endif
 }
 
+// Three CTAs per SM (<= 85 registers) pay off except for the radix-16 schedules, whose
+// butterflies need the registers (measured: 372 = 31*3*4 gains 8 %, 256 = 16*16 loses 12 %).
+template <class S> __host__ __device__ constexpr int cols_min_ctas() {
+  for (int j = 0; j < S::NS; ++j)
+    if (S::radix(j) == 16) return 2;
+  return 3;
+}
 template <class S, bool MULTI>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, cols_min_ctas<S>())
 k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int D, int d0, int u0,
               int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
   GNSSACQ_DYN_SMEM(float2, tile);
@@ -282,6 +289,137 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
   }
 }
 
+// =========================================================================== forward kernels
+// Same two-kernel four-step as k_fwd_cols / k_fwd_rows with the schedule as a template
+// parameter. Forward stages are decimation-in-frequency: butterfly, then twiddle the outputs.
+template <class S, int J, int ES, int CS>
+__device__ __forceinline__ void fwd_stage_smem(float2* tile, int ncols, const float2* __restrict__ twbase, int twoff) {
+  constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
+  const int tc = threadIdx.x & (kTW - 1);
+  if constexpr (is_split_radix(R)) {
+    stage_tile_split<R, false, ES, CS>(tile, ncols, S::F, m, twbase);
+  } else {
+    const int tb = threadIdx.x / kTW;
+    constexpr int nb = kThreads / kTW;
+    const float2* tws = twbase + twoff;
+    if (tc < ncols) {
+#pragma unroll 2
+      for (int bf = tb; bf < nbf; bf += nb) {
+        const int blk = bf / m, i = bf - blk * m;
+        float2* p = tile + (blk * R * m + i) * ES + tc * CS;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = p[q * m * ES];
+        Dft<R>::run(v);
+        if constexpr (m > 1) {
+          const float2* w = tws + i * (R - 1);
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(&w[q - 1]));
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) p[q * m * ES] = v[q];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class S, int J, int JEND, int ES, int CS>
+__device__ __forceinline__ void fwd_stages_smem(float2* tile, int ncols, const SubPlan& sp) {
+  if constexpr (J <= JEND) {
+    fwd_stage_smem<S, J, ES, CS>(tile, ncols, sp.tw, sp.tws_off[J]);
+    fwd_stages_smem<S, J + 1, JEND, ES, CS>(tile, ncols, sp);
+  }
+}
+
+// grid = (ceil(N2/16), transforms), as k_fwd_cols. S = schedule of the length-N1 transform.
+template <class S, int SRC>
+__global__ void __launch_bounds__(kThreads, 2)
+k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ rep,
+             const double* __restrict__ freq, const float2* __restrict__ nco_tab,
+             int stride, int B, float2* __restrict__ X) {
+  GNSSACQ_DYN_SMEM(float2, tile);
+  constexpr int N1 = S::F, WP = kTileW, NS = S::NS;
+  const int N = pl.N, N2 = pl.N2;
+  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
+  constexpr int nb = kThreads / kTW;
+  const int t = blockIdx.y;
+  const int col0 = blockIdx.x * kTileW;
+  const int ncols = imin(kTileW, N2 - col0);
+  long long base;
+  double f = 0.0;
+  if (SRC == 0) { const int d = t / B, b = t - d * B; base = (long long)b * stride; f = freq[d]; }
+  else { base = (long long)t * N; }
+  constexpr int R0 = S::radix(0), m0 = S::stride(0);
+  if constexpr (is_split_radix(R0)) {
+    if (tc < ncols)
+      for (int n1 = tb; n1 < N1; n1 += nb)
+        tile[n1 * WP + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n1 * N2 + col0 + tc);
+    __syncthreads();
+    fwd_stage_smem<S, 0, WP, 1>(tile, ncols, pl.s1.tw, pl.s1.tws_off[0]);
+  } else {
+    // first stage fused with the load and the carrier wipe-off
+    const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+    if (tc < ncols) {
+#pragma unroll 2
+      for (int i = tb; i < m0; i += nb) {
+        float2 v[R0];
+#pragma unroll
+        for (int q = 0; q < R0; ++q) v[q] = load_input<SRC>(x, rep, nco_tab, f, base, (i + q * m0) * N2 + col0 + tc);
+        Dft<R0>::run(v);
+        const float2* w = tws + i * (R0 - 1);
+#pragma unroll
+        for (int q = 1; q < R0; ++q) v[q] = cmul(v[q], __ldg(&w[q - 1]));
+#pragma unroll
+        for (int q = 0; q < R0; ++q) tile[(i + q * m0) * WP + tc] = v[q];
+      }
+    }
+    __syncthreads();
+  }
+  fwd_stages_smem<S, 1, NS - 2, WP, 1>(tile, ncols, pl.s1);
+  // last stage (unit stride, no stage twiddle) fused with the four-step twiddle and the store
+  {
+    constexpr int R = S::radix(NS - 1), nbf = N1 / R;
+    float2* out = X + (long long)t * N + col0 + tc;
+    const float2* twm = pl.twm + col0 + tc;
+    if (tc < ncols) {
+#pragma unroll 2
+      for (int bf = tb; bf < nbf; bf += nb) {
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = tile[(bf * R + q) * WP + tc];
+        Dft<R>::run(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) out[(bf * R + q) * N2] = cmul(v[q], __ldg(&twm[(bf * R + q) * N2]));
+      }
+    }
+  }
+}
+
+// grid = (ceil(N1/16), transforms), as k_fwd_rows: in-place length-N2 row transforms.
+template <class S>
+__global__ void __launch_bounds__(kThreads, rows_min_ctas<S>())
+k_fwd_rows_s(DevPlan pl, float2* __restrict__ X) {
+  GNSSACQ_DYN_SMEM(float2, tile);
+  constexpr int N2 = S::F, P = rows_pitch<S>(), NS = S::NS;
+  const int N = pl.N, N1 = pl.N1;
+  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
+  constexpr int nb = kThreads / kTW;
+  const int row0 = blockIdx.x * kTileW;
+  const int nrows = imin(kTileW, N1 - row0);
+  float2* Xt = X + (long long)blockIdx.y * N + (long long)row0 * N2;
+  for (int c = tb; c < nrows; c += nb) {
+#pragma unroll 8
+    for (int e = tc; e < N2; e += kTW) tile[c * P + e] = Xt[c * N2 + e];
+  }
+  __syncthreads();
+  fwd_stages_smem<S, 0, NS - 1, 1, P>(tile, nrows, pl.s2);
+  for (int c = tb; c < nrows; c += nb) {
+#pragma unroll 8
+    for (int e = tc; e < N2; e += kTW) Xt[c * N2 + e] = tile[c * P + e];
+  }
+}
+
 // --------------------------------------------------------------------------- registry
 // Schedules exactly as fft_plan.h::make_subplan emits them (odd primes descending, then
 // powers of two as 16/8/4/2): checked against the runtime plan before use.
@@ -306,6 +444,24 @@ template <class S> inline bool schedule_matches(const SubPlan& sp) {
   for (int j = 0; j < S::NS; ++j)
     if (sp.radix[j] != S::radix(j) || sp.m[j] != S::stride(j)) return false;
   return true;
+}
+
+typedef void (*fwd_cols_fn)(DevPlan, const float2*, const float*, const double*, const float2*, int, int, float2*);
+typedef void (*fwd_rows_fn)(DevPlan, float2*);
+
+inline fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
+#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
+  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
+  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200)
+#undef GNSSACQ_TRY
+  return nullptr;
+}
+inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
+#define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
+  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250)
+#undef GNSSACQ_TRY
+  return nullptr;
 }
 
 inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
