@@ -107,7 +107,7 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
 }
 
 // Choose N = N1*N2 with both factors tile-sized and as square as possible.
-inline bool make_plan(int N, HostPlan& pl, std::string& err) {
+inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0) {
   pl = HostPlan();
   pl.N = N;
   if (N < 4) { err = "FFT length must be >= 4"; return false; }
@@ -121,8 +121,14 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err) {
   for (int a = 1; (long long)a * a <= N; ++a)
     if (N % a == 0 && N / a <= kMaxSub) { best = a; }
   if (best == 0) { err = "FFT length " + std::to_string(N) + " cannot be split into two factors <= 1024"; return false; }
-  // rows (contiguous, length N2) get the larger factor: longer coalesced runs.
+  // rows (contiguous, length N2) get the larger factor: longer coalesced runs — unless that
+  // factor holds a warp-pair radix (31): the columns kernel fuses that butterfly with the
+  // magnitude/peak epilogue, measured 5-9 % faster for 61380 = 279 x 220 and 30690 = 186 x 165.
   pl.N1 = best; pl.N2 = N / best;
+  if (pl.N1 > 1 && pl.N2 % 31 == 0 && pl.N1 % 31 != 0) std::swap(pl.N1, pl.N2);
+  if (force_n1 > 1 && N % force_n1 == 0 && force_n1 <= kMaxSub && N / force_n1 <= kMaxSub && N / force_n1 > 1) {
+    pl.N1 = force_n1; pl.N2 = N / force_n1;
+  }
   if (pl.N1 < 2) { err = "FFT length " + std::to_string(N) + " is prime; unsupported"; return false; }
   pl.large = N > kMidMax;
   if (!make_subplan(pl.N1, pl.s1) || !make_subplan(pl.N2, pl.s2)) { err = "unsupported factorisation"; return false; }

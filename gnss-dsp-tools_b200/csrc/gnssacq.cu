@@ -76,6 +76,7 @@ struct gnssacq {
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
+  int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
   bool overlap = true;                // large plans: alternate unit chunks over two streams so the
                                       // rows kernel of one chunk overlaps the columns kernel of the other
   static constexpr int kMaxLanes = 4;
@@ -120,10 +121,10 @@ void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
 }
 
 int upload_plan(gnssacq* h, int N) {
-  if (h->hp.N == N) return 0;
+  if (h->hp.N == N && h->hp.N1 == (h->force_n1 > 1 && N % h->force_n1 == 0 ? h->force_n1 : h->hp.N1)) return 0;
   HostPlan hp;
   std::string err;
-  if (!make_plan(N, hp, err)) return fail(GNSSACQ_EINVAL, err);
+  if (!make_plan(N, hp, err, h->force_n1)) return fail(GNSSACQ_EINVAL, err);
   if (int rc = h->d_tw1.ensure(hp.tw1.size() * sizeof(float2))) return rc;
   if (int rc = h->d_tw2.ensure(hp.tw2.size() * sizeof(float2))) return rc;
   if (int rc = h->d_twm.ensure(hp.twm.size() * sizeof(float2))) return rc;
@@ -466,6 +467,7 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
+  if (std::string(name) == "split_n1") { h->force_n1 = value; h->R = 0; return 0; }   // replicas must be set again
   if (std::string(name) == "lanes") {
     if (value < 1 || value > gnssacq::kMaxLanes) return fail(GNSSACQ_EINVAL, "lanes must be 1..4");
     h->nlanes = value; h->overlap = value > 1; return 0;

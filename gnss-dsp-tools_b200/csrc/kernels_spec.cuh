@@ -435,6 +435,10 @@ using S372 = Sub<372, 31, 3, 4>;
 using S440 = Sub<440, 11, 5, 8>;
 using S200 = Sub<200, 5, 5, 8>;
 using S250 = Sub<250, 5, 5, 5, 2>;
+using S248 = Sub<248, 31, 8>;
+using S496 = Sub<496, 31, 16>;
+using S660 = Sub<660, 11, 5, 3, 4>;
+using S330 = Sub<330, 11, 5, 3, 2>;
 
 typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
 typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
@@ -452,14 +456,15 @@ typedef void (*fwd_rows_fn)(DevPlan, float2*);
 inline fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
-  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200)
+  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200) GNSSACQ_TRY(S248) GNSSACQ_TRY(S496) GNSSACQ_TRY(S186) GNSSACQ_TRY(S279)
 #undef GNSSACQ_TRY
   return nullptr;
 }
 inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S660) GNSSACQ_TRY(S330) GNSSACQ_TRY(S165)
+  GNSSACQ_TRY(S220)
 #undef GNSSACQ_TRY
   return nullptr;
 }
@@ -467,14 +472,15 @@ inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S660) GNSSACQ_TRY(S330) GNSSACQ_TRY(S165)
+  GNSSACQ_TRY(S220)
 #undef GNSSACQ_TRY
   return nullptr;
 }
 inline corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return multi ? k_corr_cols_s<S, true> : k_corr_cols_s<S, false>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
-  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200)
+  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200) GNSSACQ_TRY(S248) GNSSACQ_TRY(S496) GNSSACQ_TRY(S186) GNSSACQ_TRY(S279)
 #undef GNSSACQ_TRY
   return nullptr;
 }
