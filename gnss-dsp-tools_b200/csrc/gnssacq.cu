@@ -77,6 +77,7 @@ struct gnssacq {
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
+  int force_uc = 0;                   // tuning: force the number of units per correlate launch
   bool overlap = true;                // large plans: alternate unit chunks over two streams so the
                                       // rows kernel of one chunk overlaps the columns kernel of the other
   static constexpr int kMaxLanes = 4;
@@ -322,6 +323,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
     const size_t fill = (size_t)(4 * h->num_sms + ntiles - 1) / ntiles;
     size_t uc = std::max(budget / unit_bytes, fill);
     uc = std::min(uc, std::max<size_t>(1, ((size_t)3 << 30) / unit_bytes));      // hard cap 3 GiB per lane
+    if (h->force_uc > 0) uc = (size_t)h->force_uc;
     Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, uc));
     Uc = std::min(Uc, 65535);
     if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
@@ -467,6 +469,7 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
+  if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
   if (std::string(name) == "split_n1") { h->force_n1 = value; h->R = 0; return 0; }   // replicas must be set again
   if (std::string(name) == "lanes") {
     if (value < 1 || value > gnssacq::kMaxLanes) return fail(GNSSACQ_EINVAL, "lanes must be 1..4");

@@ -53,6 +53,15 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
     const int tb = threadIdx.x / kTW;
     constexpr int nb = kThreads / kTW;
     const float2* tws = twbase + twoff;
+    // When the butterfly stride divides the 16 butterfly groups, a thread meets the same
+    // twiddle row in every iteration (i = tb mod m): load it once.
+    constexpr bool kHoist = m > 1 && nb % m == 0 && R <= 8;
+    float2 wh[kHoist ? R : 1];
+    if constexpr (kHoist) {
+      const float2* w = tws + (tb % m) * (R - 1);
+#pragma unroll
+      for (int q = 1; q < R; ++q) wh[q] = __ldg(&w[q - 1]);
+    }
     if (tc < ncols) {
 #pragma unroll 2
       for (int bf = tb; bf < nbf; bf += nb) {
@@ -61,7 +70,10 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
         float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = p[q * m * ES];
-        if constexpr (m > 1) {
+        if constexpr (kHoist) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], wh[q]);
+        } else if constexpr (m > 1) {
           const float2* w = tws + i * (R - 1);
 #pragma unroll
           for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
