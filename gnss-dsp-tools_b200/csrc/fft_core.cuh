@@ -200,6 +200,84 @@ template <int P> struct Dft {
   }
 };
 
+// Composite radices done entirely in registers, so a tile transform needs fewer
+// shared-memory passes (372 = 31 * 12 instead of 31 * 3 * 4). Coprime factors use the
+// prime-factor (Good-Thomas) index maps — no twiddles at all; 9 and 25 use Cooley-Tukey with
+// compile-time twiddles. All indices are compile-time after unrolling (pure register renaming).
+__host__ __device__ constexpr int modinv(int a, int m) {
+  a %= m;
+  for (int x = 1; x < m; ++x)
+    if ((a * x) % m == 1) return x;
+  return 1;
+}
+
+template <int R1, int R2> struct DftPFA {
+  static __device__ __forceinline__ void run(float2* v) {
+    constexpr int R = R1 * R2;
+    constexpr int e1 = R2 * modinv(R2, R1), e2 = R1 * modinv(R1, R2);     // CRT reconstruction
+    float2 t[R];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+      float2 u[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) u[n1] = v[(R2 * n1 + R1 * n2) % R];
+      Dft<R1>::run(u);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) t[k1 * R2 + n2] = u[k1];
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      float2 w[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) w[n2] = t[k1 * R2 + n2];
+      Dft<R2>::run(w);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[(k1 * e1 + k2 * e2) % R] = w[k2];
+    }
+  }
+};
+
+template <int R1, int R2> struct DftCT {
+  static __device__ __forceinline__ void run(float2* v) {
+    constexpr int R = R1 * R2;
+    float2 t[R];
+    static_for<0, R2>([&](auto N2) {
+      constexpr int n2 = decltype(N2)::value;
+      float2 u[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) u[n1] = v[R2 * n1 + n2];
+      Dft<R1>::run(u);
+      static_for<0, R1>([&](auto K1) {
+        constexpr int k1 = decltype(K1)::value;
+        if constexpr ((k1 * n2) % R == 0) t[k1 * R2 + n2] = u[k1];
+        else {
+          constexpr float wc = kTrig<R>.c[(k1 * n2) % R];
+          constexpr float ws = kTrig<R>.s[(k1 * n2) % R];
+          t[k1 * R2 + n2] = cmul(u[k1], make_float2(wc, -ws));
+        }
+      });
+    });
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      float2 w[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) w[n2] = t[k1 * R2 + n2];
+      Dft<R2>::run(w);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = w[k2];
+    }
+  }
+};
+
+template <> struct Dft<6> : DftPFA<2, 3> {};
+template <> struct Dft<10> : DftPFA<2, 5> {};
+template <> struct Dft<12> : DftPFA<4, 3> {};
+template <> struct Dft<15> : DftPFA<3, 5> {};
+template <> struct Dft<20> : DftPFA<4, 5> {};
+template <> struct Dft<22> : DftPFA<2, 11> {};
+template <> struct Dft<9> : DftCT<3, 3> {};
+template <> struct Dft<25> : DftCT<5, 5> {};
+
 // ---------------------------------------------------------------- one stage over a tile
 // Threads are viewed as (tc = tid % TW, tb = tid / TW): tc walks columns, tb walks butterflies.
 constexpr int kTW = 16;
@@ -338,11 +416,14 @@ __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F,
 }
 
 // Radix classes: kernels are instantiated per class so that power-of-two plans are not
-// register-allocated for the 31-point butterfly. 0: {2,4,8,16}; 1: + {3,5}; 2: + {7,11,13,31}.
+// register-allocated for the 31-point butterfly. 0: {2,4,8,16}; 1: + {3,5,6,9,10,12,15,20,25};
+// 2: + {7,11,13,22,31}.
 constexpr int kNumRadixClasses = 3;
 __host__ __device__ constexpr int radix_class_of(int R) {
-  return (R == 2 || R == 4 || R == 8 || R == 16) ? 0 : ((R == 3 || R == 5) ? 1 : 2);
+  return (R == 2 || R == 4 || R == 8 || R == 16) ? 0
+       : ((R == 3 || R == 5 || R == 6 || R == 9 || R == 10 || R == 12 || R == 15 || R == 20 || R == 25) ? 1 : 2);
 }
+// prime factors the planner accepts
 __host__ __device__ constexpr bool radix_supported(int R) {
   return R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 11 || R == 13 || R == 16 || R == 31;
 }
@@ -360,12 +441,20 @@ __device__ __forceinline__ void stage_dispatch(int R, float2* tile, int WP, int 
         switch (R) {
           case 3: stage_tile<3, INV>(tile, WP, ncols, F, m, tw); break;
           case 5: stage_tile<5, INV>(tile, WP, ncols, F, m, tw); break;
+          case 6: stage_tile<6, INV>(tile, WP, ncols, F, m, tw); break;
+          case 9: stage_tile<9, INV>(tile, WP, ncols, F, m, tw); break;
+          case 10: stage_tile<10, INV>(tile, WP, ncols, F, m, tw); break;
+          case 12: stage_tile<12, INV>(tile, WP, ncols, F, m, tw); break;
+          case 15: stage_tile<15, INV>(tile, WP, ncols, F, m, tw); break;
+          case 20: stage_tile<20, INV>(tile, WP, ncols, F, m, tw); break;
+          case 25: stage_tile<25, INV>(tile, WP, ncols, F, m, tw); break;
           default:
             if constexpr (RC >= 2) {
               switch (R) {
                 case 7: stage_tile<7, INV>(tile, WP, ncols, F, m, tw); break;
                 case 11: stage_tile<11, INV>(tile, WP, ncols, F, m, tw); break;
                 case 13: stage_tile<13, INV>(tile, WP, ncols, F, m, tw); break;
+                case 22: stage_tile<22, INV>(tile, WP, ncols, F, m, tw); break;
                 case 31: stage_tile_split<31, INV>(tile, ncols, F, m, tw, WP); break;
                 default: break;   // the host planner never emits other radices
               }

@@ -3,6 +3,7 @@
 #pragma once
 #include "fft_core.cuh"
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -40,23 +41,64 @@ inline std::vector<int> prime_factors(int n) {
 
 // Radix schedule for one tile transform: powers of two grouped into 16/8/4/2, odd primes
 // as themselves; large odd radices first so the cheap power-of-two stages run at unit stride.
-inline bool make_subplan(int F, HostSubPlan& sp) {
+inline bool make_subplan(int F, HostSubPlan& sp, unsigned long long disabled = 0, const std::vector<int>* forced = nullptr) {
   sp = HostSubPlan();
   sp.F = F;
   if (F < 1) return false;
-  int twos = 0;
-  std::vector<int> odd;
-  for (int p : prime_factors(F)) {
-    if (p == 2) ++twos;
-    else if (!radix_supported(p)) return false;
-    else odd.push_back(p);
+  for (int p : prime_factors(F))
+    if (!radix_supported(p)) return false;
+  // Fewest stages wins (each stage is one shared-memory pass and one barrier); among equals the
+  // cheapest butterflies (smallest radix sum). Composite radices run in registers (fft_core.cuh).
+  // (12, 20 and 22 also exist as in-register butterflies but measured slower on B200: register
+  // pressure costs a resident CTA; they stay available through gnssacq_set_schedule.)
+  static const int kStageRadices[] = {31, 25, 16, 15, 13, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+  std::vector<int> best, cur;
+  std::function<void(int, size_t)> search = [&](int rem, size_t from) {
+    if (rem == 1) {
+      auto cost = [](const std::vector<int>& v) { int c = 0; for (int r : v) c += r; return c; };
+      if (best.empty() || cur.size() < best.size() || (cur.size() == best.size() && cost(cur) < cost(best))) best = cur;
+      return;
+    }
+    if (!best.empty() && cur.size() + 1 > best.size()) return;
+    for (size_t a = from; a < sizeof(kStageRadices) / sizeof(int); ++a) {
+      const int r = kStageRadices[a];
+      if (rem % r) continue;
+      if (r < 64 && ((disabled >> r) & 1ull)) continue;      // tuning: radix switched off
+      cur.push_back(r);
+      search(rem / r, a);              // non-increasing radices: largest butterflies first
+      cur.pop_back();
+    }
+  };
+  if (F > 1) search(F, 0);
+  bool use_forced = false;
+  // schedules measured faster than the rule above (tools/ab_sched.py, bench_configs.py)
+  static const std::vector<std::vector<int>> kMeasured = {{10, 20}, {10, 25}, {11, 20}};
+  if (!disabled)
+    for (const auto& m : kMeasured) {
+      long long prod = 1;
+      for (int r : m) prod *= r;
+      if (prod == F) { best = m; use_forced = true; }
+    }
+  if (forced && !forced->empty()) {
+    long long prod = 1;
+    for (int r : *forced) prod *= r;
+    if (prod == F) { best = *forced; use_forced = true; }
   }
-  for (auto it = odd.rbegin(); it != odd.rend(); ++it) sp.radix.push_back(*it);
-  while (twos > 0) {
-    int take = (twos == 5 || twos == 6 || twos == 9) ? 3 : (twos >= 4 ? 4 : twos);
-    sp.radix.push_back(1 << take);
-    twos -= take;
+  // order (measured, tools/ab_sched.py): warp-pair radices (31) first — the columns kernel fuses
+  // stage 0 with its epilogue — then odd radices descending, then even ones descending
+  // (440 = 11*5*8, 372 = 31*3*4, 320 = 5*8*8); pure powers of two ascending (128 = 8*16), which
+  // gives the rows kernel's fused last stage the longer contiguous runs.
+  if (!use_forced) {
+    bool pow2_only = true;
+    for (int r : best) pow2_only = pow2_only && (r & (r - 1)) == 0;
+    std::sort(best.begin(), best.end(), [pow2_only](int a, int b) {
+      if (pow2_only) return a < b;
+      const int ca = a == 31 ? 0 : ((a & 1) ? 1 : 2), cb = b == 31 ? 0 : ((b & 1) ? 1 : 2);
+      if (ca != cb) return ca < cb;
+      return a > b;
+    });
   }
+  sp.radix = best;
   if (sp.radix.empty()) sp.radix.push_back(1);   // F == 1: no stage
   if (F == 1) sp.radix.clear();
   if ((int)sp.radix.size() > kMaxStages) return false;
@@ -107,7 +149,8 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
 }
 
 // Choose N = N1*N2 with both factors tile-sized and as square as possible.
-inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0) {
+inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, unsigned long long disabled = 0,
+                      const std::vector<int>* sched1 = nullptr, const std::vector<int>* sched2 = nullptr) {
   pl = HostPlan();
   pl.N = N;
   if (N < 4) { err = "FFT length must be >= 4"; return false; }
@@ -131,7 +174,7 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0) {
   }
   if (pl.N1 < 2) { err = "FFT length " + std::to_string(N) + " is prime; unsupported"; return false; }
   pl.large = N > kMidMax;
-  if (!make_subplan(pl.N1, pl.s1) || !make_subplan(pl.N2, pl.s2)) { err = "unsupported factorisation"; return false; }
+  if (!make_subplan(pl.N1, pl.s1, disabled, sched1) || !make_subplan(pl.N2, pl.s2, disabled, sched2)) { err = "unsupported factorisation"; return false; }
   for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   pl.tw1 = unit_roots(pl.s1);

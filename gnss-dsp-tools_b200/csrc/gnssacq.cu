@@ -77,6 +77,9 @@ struct gnssacq {
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
+  unsigned long long disabled_radices = 0;   // tuning: stage radices the planner may not use
+  bool plan_dirty = false;
+  std::vector<int> forced_sched[2];          // tuning: explicit stage lists for the N1 / N2 transforms
   int force_uc = 0;                   // tuning: force the number of units per correlate launch
   bool overlap = true;                // large plans: alternate unit chunks over two streams so the
                                       // rows kernel of one chunk overlaps the columns kernel of the other
@@ -122,10 +125,11 @@ void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
 }
 
 int upload_plan(gnssacq* h, int N) {
-  if (h->hp.N == N && h->hp.N1 == (h->force_n1 > 1 && N % h->force_n1 == 0 ? h->force_n1 : h->hp.N1)) return 0;
+  if (h->hp.N == N && !h->plan_dirty) return 0;
   HostPlan hp;
   std::string err;
-  if (!make_plan(N, hp, err, h->force_n1)) return fail(GNSSACQ_EINVAL, err);
+  if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1])) return fail(GNSSACQ_EINVAL, err);
+  h->plan_dirty = false;
   if (int rc = h->d_tw1.ensure(hp.tw1.size() * sizeof(float2))) return rc;
   if (int rc = h->d_tw2.ensure(hp.tw2.size() * sizeof(float2))) return rc;
   if (int rc = h->d_twm.ensure(hp.twm.size() * sizeof(float2))) return rc;
@@ -470,7 +474,14 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
   if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
-  if (std::string(name) == "split_n1") { h->force_n1 = value; h->R = 0; return 0; }   // replicas must be set again
+  if (std::string(name) == "split_n1") { h->force_n1 = value; h->R = 0; h->plan_dirty = true; return 0; }   // replicas must be set again
+  if (std::string(name) == "disable_radix") {          // value 0 clears the list
+    if (value == 0) h->disabled_radices = 0;
+    else if (value > 0 && value < 64) h->disabled_radices |= 1ull << value;
+    else return fail(GNSSACQ_EINVAL, "disable_radix: 0..63");
+    h->R = 0; h->plan_dirty = true;
+    return 0;
+  }
   if (std::string(name) == "lanes") {
     if (value < 1 || value > gnssacq::kMaxLanes) return fail(GNSSACQ_EINVAL, "lanes must be 1..4");
     h->nlanes = value; h->overlap = value > 1; return 0;
@@ -478,6 +489,13 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (std::string(name) == "scratch_mb") { if (value < 1) return fail(GNSSACQ_EINVAL, "scratch_mb"); h->scratch_bytes = (size_t)value << 20; return 0; }
   if (std::string(name) == "xchunk_mb") { if (value < 1) return fail(GNSSACQ_EINVAL, "xchunk_mb"); h->xchunk_bytes = (size_t)value << 20; return 0; }
   return fail(GNSSACQ_EINVAL, std::string("unknown option ") + name);
+}
+
+int gnssacq_set_schedule(gnssacq_t* h, int32_t which, const int32_t* radices, int32_t n) {
+  if (!h || which < 1 || which > 2 || n < 0 || (n > 0 && !radices)) return fail(GNSSACQ_EINVAL, "bad schedule arguments");
+  h->forced_sched[which - 1].assign(radices, radices + n);
+  h->R = 0; h->plan_dirty = true;
+  return 0;
 }
 
 int gnssacq_set_profiling(gnssacq_t* h, int32_t on) {

@@ -29,7 +29,7 @@ struct Sub {
   }
 };
 
-constexpr bool is_split_radix(int R) { return R >= 17; }
+constexpr bool is_split_radix(int R) { return R == 31; }
 
 // ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs
 template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
@@ -435,22 +435,20 @@ k_fwd_rows_s(DevPlan pl, float2* __restrict__ X) {
 // --------------------------------------------------------------------------- registry
 // Schedules exactly as fft_plan.h::make_subplan emits them (odd primes descending, then
 // powers of two as 16/8/4/2): checked against the runtime plan before use.
-using S128 = Sub<128, 16, 8>;
+using S128 = Sub<128, 8, 16>;
 using S256 = Sub<256, 16, 16>;
 using S512 = Sub<512, 8, 8, 8>;
 using S320 = Sub<320, 5, 8, 8>;
-using S165 = Sub<165, 11, 5, 3>;
-using S186 = Sub<186, 31, 3, 2>;
-using S220 = Sub<220, 11, 5, 4>;
-using S279 = Sub<279, 31, 3, 3>;
+using S165 = Sub<165, 15, 11>;
+using S186 = Sub<186, 31, 6>;
+using S220 = Sub<220, 11, 20>;
+using S279 = Sub<279, 31, 9>;
 using S372 = Sub<372, 31, 3, 4>;
 using S440 = Sub<440, 11, 5, 8>;
-using S200 = Sub<200, 5, 5, 8>;
-using S250 = Sub<250, 5, 5, 5, 2>;
+using S200 = Sub<200, 10, 20>;
+using S250 = Sub<250, 10, 25>;
 using S248 = Sub<248, 31, 8>;
 using S496 = Sub<496, 31, 16>;
-using S660 = Sub<660, 11, 5, 3, 4>;
-using S330 = Sub<330, 11, 5, 3, 2>;
 
 typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
 typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
@@ -475,7 +473,7 @@ inline fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
 inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S660) GNSSACQ_TRY(S330) GNSSACQ_TRY(S165)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S165)
   GNSSACQ_TRY(S220)
 #undef GNSSACQ_TRY
   return nullptr;
@@ -484,7 +482,7 @@ inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
 #define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
   GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S660) GNSSACQ_TRY(S330) GNSSACQ_TRY(S165)
+  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S165)
   GNSSACQ_TRY(S220)
 #undef GNSSACQ_TRY
   return nullptr;

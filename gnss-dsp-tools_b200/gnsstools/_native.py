@@ -38,6 +38,7 @@ def _declare(lib):
         'gnssacq_set_replicas_device': [p, p, i32, i32],
         'gnssacq_set_profiling': [p, i32],
         'gnssacq_set_option': [p, C.c_char_p, i32],
+        'gnssacq_set_schedule': [p, i32, p, i32],
         'gnssacq_get_stage_times': [p, p, p, i32],
         'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
@@ -133,6 +134,10 @@ class Engine:
 
     def set_option(self, name, value):
         self._check(self._lib.gnssacq_set_option(self._h, name.encode(), int(value)))
+
+    def set_schedule(self, which, radices):
+        r = np.ascontiguousarray(radices, dtype=np.int32)
+        self._check(self._lib.gnssacq_set_schedule(self._h, int(which), _ptr(r), r.size))
 
     def set_profiling(self, on):
         self._check(self._lib.gnssacq_set_profiling(self._h, int(bool(on))))

@@ -123,6 +123,10 @@ int gnssacq_synchronize(gnssacq_t* h);
  * streams so the rows kernel of one chunk overlaps the columns kernel of the other; 0 runs
  * every kernel back to back on the handle's stream (what per-kernel stage times need). */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
+/* Tuning: force the stage radices (forward order) of the length-N1 (which = 1) or length-N2
+ * (which = 2) tile transform; ignored when their product does not match; n = 0 restores the
+ * planner's choice. Replicas must be set again afterwards. */
+int gnssacq_set_schedule(gnssacq_t* h, int32_t which, const int32_t* radices, int32_t n);
 /* Per-stage device time: when profiling is on, CUDA events bracket the launches of each stage
  * on the handle's stream. Stages: 0 wipe-off+forward FFT, 1 correlate rows kernel (large
  * plans only), 2 correlate kernel (mid plans) / correlate columns kernel (large plans),
