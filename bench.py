@@ -203,16 +203,16 @@ def main():
 
     # ---- device-resident inputs for `value`
     x_dev = torch.from_numpy(x.view(np.float32).copy()).to(dev)
-    rep_dev = torch.from_numpy(rep).to(dev)
+    rep_dev = torch.from_numpy(rep.astype(np.float32)).to(dev)
     rec_dev = torch.zeros(R * 4, dtype=torch.int32, device=dev)
     gathered = torch.zeros(world * R * 4, dtype=torch.int32, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     # ---- pinned host inputs for `e2e`
     x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
-    rep_pin = torch.from_numpy(rep).pin_memory()
+    rep_pin = torch.from_numpy(rep).pin_memory()                       # int8 replicas: +-1
     rec_pin = torch.zeros(R * 4, dtype=torch.int32).pin_memory()
     x_dev2 = torch.empty_like(x_dev)
-    rep_dev2 = torch.empty_like(rep_dev)
+    rep_dev2 = torch.empty(rep.shape, dtype=torch.int8, device=dev)
 
     def step_resident():
         eng.set_signal_device(x_dev.data_ptr(), x.size)
@@ -225,7 +225,7 @@ def main():
         x_dev2.copy_(x_pin, non_blocking=True)
         rep_dev2.copy_(rep_pin, non_blocking=True)
         eng.set_signal_device(x_dev2.data_ptr(), x.size)
-        eng.set_replicas_device(rep_dev2.data_ptr(), R, N)
+        eng.set_replicas_i8_device(rep_dev2.data_ptr(), R, N)
         eng.search_device(my_f, N, 1, True, N_LAGS, rec_dev.data_ptr())
         if world > 1:
             dist.all_gather_into_tensor(gathered, rec_dev)

@@ -463,6 +463,31 @@ int gnssacq_set_replicas(gnssacq_t* h, const float* replicas, int32_t R, int32_t
   return replicas_from_device(h, h->d_tmp.as<float>(), R, N);
 }
 
+static int replicas_from_device_i8(gnssacq_t* h, const signed char* d_i8, int32_t R, int32_t N) {
+  const size_t nel = (size_t)R * N;
+  if (int rc = h->d_tmp.ensure(nel * sizeof(float))) return rc;
+  const int blocks = (int)std::min<size_t>((nel + kThreads - 1) / kThreads, (size_t)h->num_sms * 16);
+  GNSSACQ_LAUNCH(k_i8_to_f32, dim3(blocks), dim3(kThreads), 0, h->stream, d_i8, (long long)nel, h->d_tmp.as<float>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return replicas_from_device(h, h->d_tmp.as<float>(), R, N);
+}
+
+int gnssacq_set_replicas_i8(gnssacq_t* h, const int8_t* replicas, int32_t R, int32_t N) {
+  if (!h || !replicas || R <= 0 || N <= 0) return fail(GNSSACQ_EINVAL, "bad replica arguments");
+  CU(cudaSetDevice(h->device));
+  const size_t nel = (size_t)R * N;
+  if (int rc = h->d_raw.ensure(nel)) return rc;
+  CU(cudaMemcpyAsync(h->d_raw.p, replicas, nel, cudaMemcpyHostToDevice, h->stream));
+  return replicas_from_device_i8(h, h->d_raw.as<signed char>(), R, N);
+}
+
+int gnssacq_set_replicas_i8_device(gnssacq_t* h, const void* device_replicas_i8, int32_t R, int32_t N) {
+  if (!h || !device_replicas_i8 || R <= 0 || N <= 0) return fail(GNSSACQ_EINVAL, "bad replica arguments");
+  CU(cudaSetDevice(h->device));
+  return replicas_from_device_i8(h, static_cast<const signed char*>(device_replicas_i8), R, N);
+}
+
 int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32_t R, int32_t N) {
   if (!h || !device_replicas || R <= 0 || N <= 0) return fail(GNSSACQ_EINVAL, "bad replica arguments");
   CU(cudaSetDevice(h->device));

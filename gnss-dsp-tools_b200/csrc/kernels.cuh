@@ -357,6 +357,13 @@ k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normali
   }
 }
 
+// int8 replicas (+-1 / 0) -> float32: lets callers ship a quarter of the bytes over PCIe.
+__global__ void __launch_bounds__(kThreads)
+k_i8_to_f32(const signed char* __restrict__ in, long long n, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i];
+}
+
 // ============================================================================ capture mix
 // In-place whole-capture carrier wipe-off, reference gnsstools/nco.py:30-41: int64 phase
 // accumulator scaled by 2^50 (closed form dp_i = dp0 + i*df, wrapping), complex128 table,

@@ -36,6 +36,8 @@ def _declare(lib):
         'gnssacq_set_signal_device': [p, p, i64],
         'gnssacq_set_replicas': [p, p, i32, i32],
         'gnssacq_set_replicas_device': [p, p, i32, i32],
+        'gnssacq_set_replicas_i8': [p, p, i32, i32],
+        'gnssacq_set_replicas_i8_device': [p, p, i32, i32],
         'gnssacq_set_profiling': [p, i32],
         'gnssacq_set_option': [p, C.c_char_p, i32],
         'gnssacq_set_schedule': [p, i32, p, i32],
@@ -122,11 +124,21 @@ class Engine:
         self.n_samples = int(n_samples)
 
     def set_replicas(self, replicas):
-        rep = np.ascontiguousarray(replicas, dtype=np.float32)
+        """R x N time-domain replicas. int8 arrays (+-1 / 0) travel as int8, anything else as float32."""
+        rep = np.asarray(replicas)
         if rep.ndim != 2:
             raise ValueError('replicas must be R x N')
-        self._check(self._lib.gnssacq_set_replicas(self._h, _ptr(rep), rep.shape[0], rep.shape[1]))
+        if rep.dtype == np.int8:
+            rep = np.ascontiguousarray(rep)
+            self._check(self._lib.gnssacq_set_replicas_i8(self._h, _ptr(rep), rep.shape[0], rep.shape[1]))
+        else:
+            rep = np.ascontiguousarray(rep, dtype=np.float32)
+            self._check(self._lib.gnssacq_set_replicas(self._h, _ptr(rep), rep.shape[0], rep.shape[1]))
         self.R, self.N = rep.shape
+
+    def set_replicas_i8_device(self, device_ptr, R, N):
+        self._check(self._lib.gnssacq_set_replicas_i8_device(self._h, C.c_void_p(int(device_ptr)), int(R), int(N)))
+        self.R, self.N = int(R), int(N)
 
     def set_replicas_device(self, device_ptr, R, N):
         self._check(self._lib.gnssacq_set_replicas_device(self._h, C.c_void_p(int(device_ptr)), int(R), int(N)))

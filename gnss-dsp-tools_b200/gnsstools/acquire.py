@@ -107,7 +107,7 @@ def replica(sig, key):
     c = mod.code(0, 0, incr, sig.n) if sig.fdma else mod.code(key, 0, 0, incr, sig.n)
     if sig.boc:
         c = c * nco.boc11(0, 0, incr, sig.n)
-    out = np.zeros(sig.N, dtype=np.float32)
+    out = np.zeros(sig.N, dtype=np.int8)          # +-1 and 0 exactly; int8 keeps the upload small
     out[:sig.n] = c
     return out
 

@@ -72,6 +72,11 @@ int gnssacq_set_replicas(gnssacq_t* h, const float* replicas, int32_t R, int32_t
  * the stream work, so keep it alive until the stream has drained). */
 int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32_t R, int32_t N);
 
+/* Replicas as int8 (+1, -1, 0 — what code()/boc11()/zero padding produce), host or device: a
+ * quarter of the bytes of the float32 form; converted on the device, same result. */
+int gnssacq_set_replicas_i8(gnssacq_t* h, const int8_t* replicas, int32_t R, int32_t N);
+int gnssacq_set_replicas_i8_device(gnssacq_t* h, const void* device_replicas_i8, int32_t R, int32_t N);
+
 /* The Doppler x block loops of search() for every replica at once.
  *   nco_freq[D]   wipe-off frequency per Doppler bin in cycles/sample, i.e. the float64
  *                 value -doppler/fs (or -(562500*chan+doppler)/fs, acquire-glonass-l1.py:28)
