@@ -148,7 +148,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'correlation cells/s (PRNxDopplerxcode-phase)', 'value': value, 'unit': 'cells/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': info['sample']},
+        'config': {'workload': WORKLOAD, 'R': R, 'D_per_gpu': D_PER_GPU, 'N': N, 'B': 1, 'sample': info['sample']},
         'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': info['cores'], 'kind': 'port', 'sample': info['sample']},
         'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
