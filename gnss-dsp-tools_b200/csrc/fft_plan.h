@@ -26,6 +26,8 @@ struct HostPlan {
   int N = 0, N1 = 0, N2 = 0;
   bool large = false;                // two kernels through an L2-resident scratch
   int rclass = 0;                    // radix class of the kernels to launch (fft_core.cuh)
+  bool cube = false;                 // N == 4096: the 16x16x16 single-CTA kernels (kernels_cube.cuh)
+  std::vector<float2> cube_tw0, cube_tw1;
   HostSubPlan s1, s2;                // s1: length N1 over stride-N2 columns; s2: length N2 over rows
   std::vector<float2> tw1, tw2;      // exp(-2 pi i k / F)
   std::vector<float2> twm;           // twm[p1*N2 + n2] = exp(-2 pi i k1(p1) n2 / N)
@@ -174,6 +176,21 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
   }
   if (pl.N1 < 2) { err = "FFT length " + std::to_string(N) + " is prime; unsupported"; return false; }
   pl.large = N > kMidMax;
+  pl.cube = (N == 4096) && force_n1 == 0 && disabled == 0;
+  if (pl.cube) {
+    pl.cube_tw0.resize(15 * 256);
+    pl.cube_tw1.resize(15 * 16);
+    for (int q = 1; q < 16; ++q) {
+      for (int t = 0; t < 256; ++t) {
+        double a = -2.0 * M_PI * (double)(q * t) / 4096.0;
+        pl.cube_tw0[(q - 1) * 256 + t] = make_float2((float)cos(a), (float)sin(a));
+      }
+      for (int c = 0; c < 16; ++c) {
+        double a = -2.0 * M_PI * (double)(q * c) / 256.0;
+        pl.cube_tw1[(q - 1) * 16 + c] = make_float2((float)cos(a), (float)sin(a));
+      }
+    }
+  }
   if (!make_subplan(pl.N1, pl.s1, disabled, sched1) || !make_subplan(pl.N2, pl.s2, disabled, sched2)) { err = "unsupported factorisation"; return false; }
   for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));

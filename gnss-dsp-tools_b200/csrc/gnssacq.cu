@@ -3,6 +3,7 @@
 #include "fft_plan.h"
 #include "kernels_spec.cuh"
 #include "preprocess.cuh"
+#include "kernels_cube.cuh"
 
 #include <algorithm>
 #include <new>
@@ -66,7 +67,8 @@ struct gnssacq {
 
   HostPlan hp;
   DevPlan dp{};
-  DevBuf d_tw1, d_tw2, d_twm;
+  DevBuf d_tw1, d_tw2, d_twm, d_cube0, d_cube1;
+  CubeTw cube_tw{nullptr, nullptr};
   DevBuf d_C;                         // replica spectra [R][N]
   int R = 0, N = 0;
 
@@ -136,6 +138,14 @@ int upload_plan(gnssacq* h, int N) {
   CU(cudaMemcpyAsync(h->d_tw1.p, hp.tw1.data(), hp.tw1.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_tw2.p, hp.tw2.data(), hp.tw2.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_twm.p, hp.twm.data(), hp.twm.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  if (hp.cube) {
+    if (int rc = h->d_cube0.ensure(hp.cube_tw0.size() * sizeof(float2))) return rc;
+    if (int rc = h->d_cube1.ensure(hp.cube_tw1.size() * sizeof(float2))) return rc;
+    CU(cudaMemcpyAsync(h->d_cube0.p, hp.cube_tw0.data(), hp.cube_tw0.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_cube1.p, hp.cube_tw1.data(), hp.cube_tw1.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    h->cube_tw.tw0 = h->d_cube0.as<float2>();
+    h->cube_tw.tw1 = h->d_cube1.as<float2>();
+  }
   CU(cudaStreamSynchronize(h->stream));
   h->dp.N = hp.N; h->dp.N1 = hp.N1; h->dp.N2 = hp.N2;
   fill_subplan(hp.s1, h->d_tw1.as<float2>(), h->dp.s1);
@@ -201,7 +211,11 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
     const DevPlan& p = h->dp;
     const float2* tab = h->d_nco_f32.as<float2>();
     StageTimer timer(h, kStageFwd, h->hp.large ? 2 : 1);
-    if (!h->hp.large) {
+    if (h->hp.cube && h->use_spec) {
+      auto kern = k_fwd_cube<SRC>;
+      GNSSACQ_LAUNCH(kern, dim3(nt), dim3(256), (size_t)kCubeSmem, h->stream, h->cube_tw, h->d_x, rep, d_freq, tab, stride, B, X);
+      h->launches += 1;
+    } else if (!h->hp.large) {
       const size_t sm = mid_smem(p, false);
       auto kern = k_fwd_mid<RC, SRC>;
       if (int rc2 = allow_smem(h, kern, sm)) return rc2;
@@ -231,7 +245,16 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
     constexpr int RC = decltype(rc)::value;
     const DevPlan& p = h->dp;
     const int R = h->R;
-    if (!h->hp.large) {
+    if (h->hp.cube && h->use_spec) {
+      StageTimer timer(h, kStageCorrCols, 1);
+      if (B > 1)
+        GNSSACQ_LAUNCH(k_corr_cube<true>, dim3(R * dc), dim3(256), (size_t)kCubeSmem, h->stream, h->cube_tw, h->d_X.as<float2>(),
+                       h->d_C.as<float2>(), R, B, D, d0, n_lags, scale, h->d_parts.as<Part>(), d_qdump);
+      else
+        GNSSACQ_LAUNCH(k_corr_cube<false>, dim3(R * dc), dim3(256), (size_t)kCubeSmem, h->stream, h->cube_tw, h->d_X.as<float2>(),
+                       h->d_C.as<float2>(), R, B, D, d0, n_lags, scale, h->d_parts.as<Part>(), d_qdump);
+      h->launches += 1;
+    } else if (!h->hp.large) {
       const size_t sm = mid_smem(p, B > 1);
       auto kern = k_corr_mid<RC>;
       if (int rc2 = allow_smem(h, kern, sm)) return rc2;
@@ -393,7 +416,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_C, &h->d_X,
+  for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
                     &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128})
     b->release();
@@ -656,6 +679,7 @@ int64_t gnssacq_launch_count(gnssacq_t* h) { return h ? h->launches : 0; }
 
 int gnssacq_kernel_variant(gnssacq_t* h) {
   if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
+  if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
   return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0);
 }

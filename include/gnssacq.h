@@ -118,7 +118,8 @@ int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq_int8, int64_t n_samples, d
 int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
 /* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =
- * specialised columns kernel; 0 = generic runtime-planned kernels. Negative on error. */
+ * specialised columns kernel; 4 = the 16x16x16 single-CTA kernels (N = 4096); 0 = generic
+ * runtime-planned kernels. Negative on error. */
 int gnssacq_kernel_variant(gnssacq_t* h);
 int gnssacq_synchronize(gnssacq_t* h);
 /* Tuning switches, for tests and A/B measurements. "specialized_kernels" (default 1): use the
