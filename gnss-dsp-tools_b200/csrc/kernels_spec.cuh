@@ -30,6 +30,8 @@ struct Sub {
 };
 
 constexpr bool is_split_radix(int R) { return R == 31; }
+// butterflies a thread keeps in flight per loop trip: small radices need several for ILP
+constexpr int stage_unroll(int R) { return R <= 5 ? 4 : (R <= 10 ? 2 : 1); }
 
 // ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs
 template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
@@ -63,7 +65,7 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
       for (int q = 1; q < R; ++q) wh[q] = __ldg(&w[q - 1]);
     }
     if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R)
       for (int bf = tb; bf < nbf; bf += nb) {
         const int blk = bf / m, i = bf - blk * m;
         float2* p = tile + (blk * R * m + i) * ES + tc * CS;
@@ -211,7 +213,7 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
     {
       constexpr int R = S::radix(NS - 1), nbf = N1 / R;
       if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R)
         for (int bf = tb; bf < nbf; bf += nb) {
           float2 v[R];
 #pragma unroll
@@ -273,7 +275,7 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
     } else {
       const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
       if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R0)
         for (int i = tb; i < m0; i += nb) {
           const float2* p = tile + i * WP + tc;
           float2 v[R0];
@@ -315,7 +317,7 @@ __device__ __forceinline__ void fwd_stage_smem(float2* tile, int ncols, const fl
     constexpr int nb = kThreads / kTW;
     const float2* tws = twbase + twoff;
     if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R)
       for (int bf = tb; bf < nbf; bf += nb) {
         const int blk = bf / m, i = bf - blk * m;
         float2* p = tile + (blk * R * m + i) * ES + tc * CS;
@@ -373,7 +375,7 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
     // first stage fused with the load and the carrier wipe-off
     const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
     if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R0)
       for (int i = tb; i < m0; i += nb) {
         float2 v[R0];
 #pragma unroll
@@ -395,7 +397,7 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
     float2* out = X + (long long)t * N + col0 + tc;
     const float2* twm = pl.twm + col0 + tc;
     if (tc < ncols) {
-#pragma unroll 2
+#pragma unroll stage_unroll(R)
       for (int bf = tb; bf < nbf; bf += nb) {
         float2 v[R];
 #pragma unroll

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""A few small searches covering every kernel family, for compute-sanitizer (memcheck / racecheck):
+  compute-sanitizer --tool racecheck python tools/sanitize_cases.py"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'gnss-dsp-tools_b200')]
+from gnsstools import _native
+eng = _native.Engine(0)
+rng = np.random.default_rng(0)
+# name, n, pad, R, D, B, normalize, spec
+CASES = [('cube 4096', 4096, False, 2, 3, 2, True, 1), ('mid generic 4096', 4096, False, 1, 2, 2, True, 0),
+         ('mid 2310 (3,5,7,11)', 2310, False, 1, 2, 1, False, 1), ('mid 4092 (31)', 4092, False, 1, 2, 1, False, 1),
+         ('large 16384 spec', 8192, True, 2, 2, 2, False, 1), ('large 30690 spec (31,6 / 15,11)', 15345, True, 2, 2, 2, False, 1),
+         ('large 61380 spec', 30690, True, 1, 2, 2, False, 1), ('large 163680 spec', 163680, False, 1, 2, 1, True, 1),
+         ('large 163680 generic', 163680, False, 1, 1, 1, True, 0), ('large 50000 spec', 25000, True, 1, 2, 2, False, 1)]
+for name, n, pad, R, D, B, norm, spec in CASES:
+    N = 2 * n if pad else n
+    nx = (B - 1) * n + N
+    x = (rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)).astype(np.complex64)
+    rep = np.where(rng.integers(0, 2, (R, N)) > 0, 1, -1).astype(np.int8)
+    eng.set_option('specialized_kernels', spec)
+    eng.set_signal(x); eng.set_replicas(rep)
+    m, l, d = eng.search(-np.arange(D) * 1e-5, n, B, norm)
+    print(name, 'variant', eng.kernel_variant(), m[:2], l[:2], d[:2], flush=True)
+raw = rng.integers(-127, 128, 2 * 40000).astype(np.int8)
+eng.preprocess(raw, -0.01, 0.0, np.ones(161) / 161, 1.25, 20000)
+xs = (rng.normal(0, 8, 5000) + 1j * rng.normal(0, 8, 5000)).astype(np.complex64)
+eng.mix(xs, 0.123, 0.0)
+print('front end + mix done')
