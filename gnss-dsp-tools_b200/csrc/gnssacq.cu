@@ -1,9 +1,11 @@
 // libgnssacq.so — C ABI (include/gnssacq.h) over the sm_100a acquisition kernels.
 #include "../../include/gnssacq.h"
 #include "fft_plan.h"
-#include "kernels_spec.cuh"
+#include "kernels.cuh"
+#include "registry.h"
 #include "preprocess.cuh"
 #include "kernels_cube.cuh"
+#include "bank.cuh"
 
 #include <algorithm>
 #include <new>
@@ -74,10 +76,12 @@ struct gnssacq {
 
   DevBuf d_X, d_scratch, d_parts, d_freq, d_rec, d_q, d_tmp;
   DevBuf d_raw, d_ext, d_y1, d_z, d_fir, d_pre128;        // capture front end
+  DevBuf d_chips, d_base, d_bank;                         // replica builder / correlator bank
 
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
+  int small_ctas = 3;                 // bit 0: 8-row / 128-160-thread rows kernel, bit 1: 128-thread columns kernel
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
   unsigned long long disabled_radices = 0;   // tuning: stage radices the planner may not use
   bool plan_dirty = false;
@@ -263,13 +267,24 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
                      h->d_C.as<float2>(), R, B, D, d0, n_lags, scale, h->d_parts.as<Part>(), d_qdump);
       h->launches += 1;
     } else {
-      const size_t smr = rows_smem(p), smc = cols_smem(p, B > 1);
+      size_t smr = rows_smem(p);
+      const size_t smc = cols_smem(p, B > 1);
       corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2) : nullptr;
       corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1, B > 1) : nullptr;
+      int tr = kThreads, tcn = kThreads, row_tile = kTileW;
+      if (h->use_spec && (h->small_ctas & 1)) {
+        const RowsSmall rs = find_rows_small(p.s2);
+        if (rs.fn) { kr = rs.fn; tr = rs.threads; smr = rs.smem; row_tile = kRowsSmallTile; }
+      }
+      if (h->use_spec && (h->small_ctas & 2)) {
+        const ColsSmall cs = find_cols_small(p.s1, B > 1);
+        if (cs.fn) { kc = cs.fn; tcn = cs.threads; }
+      }
       if (!kr) kr = k_corr_rows<RC>;
       if (!kc) kc = k_corr_cols<RC>;
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
       if (int rc2 = allow_smem(h, kc, smc)) return rc2;
+      const int nrt = (p.N1 + row_tile - 1) / row_tile;
       const int units = R * dc;
       const bool two_lanes = h->overlap && units > Uc;
       if (two_lanes) {
@@ -282,9 +297,9 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
           const int uc = std::min(Uc, units - u0);
           cudaStream_t st = h->lane[k % h->nlanes];
           float2* scr = h->d_scratch_lane[k % h->nlanes].as<float2>();
-          GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, st,
+          GNSSACQ_LAUNCH(kr, dim3(nrt, B, uc), dim3(tr), smr, st,
                          p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, scr);
-          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
+          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(tcn), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
                          ntiles, h->d_parts.as<Part>(), d_qdump);
           nl += 2;
         }
@@ -299,11 +314,11 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
           const int uc = std::min(Uc, units - u0);
           {
             StageTimer timer(h, kStageCorrRows, 1);
-            GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, B, uc), dim3(kThreads), smr, h->stream,
+            GNSSACQ_LAUNCH(kr, dim3(nrt, B, uc), dim3(tr), smr, h->stream,
                            p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
           }
           StageTimer timer(h, kStageCorrCols, 1);
-          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(kThreads), smc, h->stream, p,
+          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(tcn), smc, h->stream, p,
                          h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
                          h->d_parts.as<Part>(), d_qdump);
           h->launches += 2;
@@ -418,7 +433,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -517,10 +532,61 @@ int gnssacq_set_replicas_device(gnssacq_t* h, const void* device_replicas, int32
   return replicas_from_device(h, static_cast<const float*>(device_replicas), R, N);
 }
 
+int gnssacq_set_replicas_from_chips(gnssacq_t* h, const int8_t* chips01, int32_t R, int32_t L, int32_t n, int32_t N,
+                                    double base, double incr, int32_t boc, double base2) {
+  if (!h || !chips01 || R <= 0 || L <= 0 || n <= 0 || N < n) return fail(GNSSACQ_EINVAL, "bad replica arguments");
+  if (R > 65535) return fail(GNSSACQ_EINVAL, "too many replicas for one call");
+  CU(cudaSetDevice(h->device));
+  if (int rc = h->d_chips.ensure((size_t)R * L)) return rc;
+  if (int rc = h->d_tmp.ensure((size_t)R * N * sizeof(float))) return rc;
+  CU(cudaMemcpyAsync(h->d_chips.p, chips01, (size_t)R * L, cudaMemcpyHostToDevice, h->stream));
+  GNSSACQ_LAUNCH(k_build_replicas, dim3((N + kThreads - 1) / kThreads, R), dim3(kThreads), 0, h->stream,
+                 h->d_chips.as<signed char>(), L, n, N, base, incr, boc, base2, h->d_tmp.as<float>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return replicas_from_device(h, h->d_tmp.as<float>(), R, N);
+}
+
+int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, double nco_freq, int32_t n,
+                           int32_t n_blocks, int32_t block_stride, const double* base, int32_t H, double incr,
+                           double* out_c128) {
+  if (!h || !chips01 || !base || !out_c128 || L <= 0 || n <= 0 || n_blocks <= 0 || block_stride < 0 || H <= 0)
+    return fail(GNSSACQ_EINVAL, "bad correlator-bank arguments");
+  if (n_blocks > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
+  if (!h->d_x) return fail(GNSSACQ_ESTATE, "gnssacq_set_signal has not been called");
+  if ((int64_t)(n_blocks - 1) * block_stride + n > h->n_x)
+    return fail(GNSSACQ_EINVAL, "capture too short: need (n_blocks-1)*block_stride + n = " +
+                                    std::to_string((int64_t)(n_blocks - 1) * block_stride + n) + " samples, have " + std::to_string(h->n_x));
+  CU(cudaSetDevice(h->device));
+  const size_t nhb = (size_t)H * n_blocks;
+  if (int rc = h->d_chips.ensure((size_t)L)) return rc;
+  if (int rc = h->d_base.ensure(nhb * sizeof(double))) return rc;
+  if (int rc = h->d_bank.ensure(nhb * sizeof(double2))) return rc;
+  if (int rc = h->d_scratch.ensure((size_t)n_blocks * n * sizeof(float2))) return rc;
+  CU(cudaMemcpyAsync(h->d_chips.p, chips01, (size_t)L, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_base.p, base, nhb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  GNSSACQ_LAUNCH(k_bank_wipeoff, dim3((n + kThreads - 1) / kThreads, n_blocks), dim3(kThreads), 0, h->stream,
+                 h->d_x, h->d_nco_f32.as<float2>(), nco_freq, n, block_stride, h->d_scratch.as<float2>());
+  h->launches += 1;
+  // grid.x carries the hypotheses in slices (any H), grid.y the blocks
+  for (int h0 = 0; h0 < H; h0 += 32768) {
+    const int hc = std::min(32768, H - h0);
+    GNSSACQ_LAUNCH(k_corr_bank, dim3(hc, n_blocks), dim3(kThreads), 0, h->stream, h->d_scratch.as<float2>(),
+                   h->d_chips.as<signed char>(), L, n, n_blocks, h->d_base.as<double>() + (size_t)h0 * n_blocks, incr,
+                   h->d_bank.as<double2>() + (size_t)h0 * n_blocks);
+    h->launches += 1;
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_c128, h->d_bank.p, nhb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
+  if (std::string(name) == "small_ctas") { h->small_ctas = value; return 0; }
   if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
   if (std::string(name) == "split_n1") { h->force_n1 = value; h->R = 0; h->plan_dirty = true; return 0; }   // replicas must be set again
   if (std::string(name) == "disable_radix") {          // value 0 clears the list

@@ -324,7 +324,7 @@ k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D,
 // doppler bin with the reference's rule — strict '>' scanning ascending bins from 0, so ties
 // go to the lowest bin and nothing is selected unless some metric is > 0
 // (acquire-gps-l1.py:25,36-39).
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normalize, Record* __restrict__ out) {
   const int r = blockIdx.x;
   unsigned long long best = 0ull;
@@ -358,7 +358,7 @@ k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normali
 }
 
 // int8 replicas (+-1 / 0) -> float32: lets callers ship a quarter of the bytes over PCIe.
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_i8_to_f32(const signed char* __restrict__ in, long long n, float* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i];
@@ -368,7 +368,7 @@ k_i8_to_f32(const signed char* __restrict__ in, long long n, float* __restrict__
 // In-place whole-capture carrier wipe-off, reference gnsstools/nco.py:30-41: int64 phase
 // accumulator scaled by 2^50 (closed form dp_i = dp0 + i*df, wrapping), complex128 table,
 // complex128 product rounded to complex64 on store.
-__global__ void __launch_bounds__(kThreads, 2)
+static __global__ void __launch_bounds__(kThreads, 2)
 k_mix(float2* __restrict__ x, long long n, unsigned long long dp0, unsigned long long df,
       const double2* __restrict__ tab) {
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -45,7 +45,7 @@ template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
 // ---- one in-shared-memory inverse stage (stage J of S). Element e of column c lives at
 // tile[e*ES + c*CS]: the columns kernel uses (ES, CS) = (16, 1), the rows kernel (1, odd pitch)
 // — either way the 16 lanes of a half-warp (consecutive c) hit 16 distinct bank pairs.
-template <class S, int J, int ES, int CS>
+template <class S, int J, int ES, int CS, int THREADS = kThreads>
 __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const float2* __restrict__ twbase, int twoff) {
   constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
   const int tc = threadIdx.x & (kTW - 1);
@@ -53,7 +53,7 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
     stage_tile_split<R, true, ES, CS>(tile, ncols, S::F, m, twbase);   // warp-pair version, W_F table
   } else {
     const int tb = threadIdx.x / kTW;
-    constexpr int nb = kThreads / kTW;
+    constexpr int nb = THREADS / kTW;
     const float2* tws = twbase + twoff;
     // When the butterfly stride divides the 16 butterfly groups, a thread meets the same
     // twiddle row in every iteration (i = tb mod m): load it once.
@@ -89,11 +89,11 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
   __syncthreads();
 }
 
-template <class S, int J, int JEND, int ES, int CS>
+template <class S, int J, int JEND, int ES, int CS, int THREADS = kThreads>
 __device__ __forceinline__ void inv_stages_smem(float2* tile, int ncols, const SubPlan& sp) {
   if constexpr (J >= JEND) {
-    inv_stage_smem<S, J, ES, CS>(tile, ncols, sp.tw, sp.tws_off[J]);
-    inv_stages_smem<S, J - 1, JEND, ES, CS>(tile, ncols, sp);
+    inv_stage_smem<S, J, ES, CS, THREADS>(tile, ncols, sp.tw, sp.tws_off[J]);
+    inv_stages_smem<S, J - 1, JEND, ES, CS, THREADS>(tile, ncols, sp);
   }
 }
 
@@ -178,6 +178,112 @@ __device__ __forceinline__ float sqrt_fast(float a) {
 #endif
 }
 
+// Last inverse stage of the columns transform fused with |.|, the non-coherent sum and the
+// running peak search (shared by the one-tile-per-CTA and the pipelined columns kernels).
+// Per-thread state: best / bestlag / sum over the eligible lags, unscaled.
+// SPLIT: share a radix-31 butterfly between two warps (halves its live registers; needed at 256
+// threads x 3 CTAs per SM). With 128-thread CTAs the butterfly fits in one thread's 128 registers
+// and the duplicated loads / twiddle multiplies of the shared form go away.
+template <class S, bool MULTI, int THREADS = kThreads, bool SPLIT = true>
+__device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, const DevPlan& pl, int ncols, int lag0,
+                                                int b, bool last, int n_lags, float scale, float* qd,
+                                                float& best, int& bestlag, float& sum) {
+  constexpr int WP = kTileW;
+  const int N2 = pl.N2;
+  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
+  constexpr int nb = THREADS / kTW;
+  const bool dump = qd != nullptr;
+  constexpr int R0 = S::radix(0), m0 = S::stride(0);
+  auto sink = [&](int n1, float2 v) {
+    float acc = sqrt_fast(v.x * v.x + v.y * v.y);
+    if (MULTI) {
+      if (b > 0) acc += qs[n1 * WP + tc];
+      if (!last) { qs[n1 * WP + tc] = acc; return; }
+    }
+    sum += acc;
+    if (acc >= best) {                       // rare after the first few samples
+      const int lag = n1 * N2 + lag0;
+      if (lag < n_lags && (acc > best || lag < bestlag)) { best = acc; bestlag = lag; }
+    }
+    if (dump) qd[n1 * N2 + lag0] = acc * scale;
+  };
+  if constexpr (is_split_radix(R0) && SPLIT) {
+    // warp-pair butterfly (see stage_tile_split): both warps load, each emits half the outputs
+    constexpr int H = (R0 - 1) / 2, KA = (H + 1) / 2;
+    const int warp = threadIdx.x >> 5, role = warp & 1;
+    const int slot = (warp >> 1) * 2 + ((threadIdx.x >> 4) & 1);
+    constexpr int nslots = THREADS >> 5;
+    const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+    for (int i = slot; i < m0; i += nslots) {
+      if (tc < ncols) {
+        const float2* p = tile + i * WP + tc;
+        const float2* w = tws + i * (R0 - 1);
+        float2 a[H + 1], bq[H + 1];
+        const float2 x0 = cswap(p[0]);
+        static_for<1, H + 1>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
+          const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
+          a[j] = cadd(s, t);
+          bq[j] = csub(s, t);
+        });
+        auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };      // |.| ignores the re/im swap
+        if (role == 0) {
+          float2 s0 = x0;
+          static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
+          emit(0, s0);
+          prime_outputs<R0, 1, KA>(x0, a, bq, emit);
+        } else {
+          prime_outputs<R0, KA + 1, H>(x0, a, bq, emit);
+        }
+      }
+    }
+  } else if constexpr (R0 >= 11 && R0 % 2 == 1) {
+    // large prime, one thread per butterfly: outputs go straight into the sink, never into registers
+    constexpr int H = (R0 - 1) / 2;
+    const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+    if (tc < ncols) {
+      for (int i = tb; i < m0; i += nb) {
+        const float2* p = tile + i * WP + tc;
+        const float2* w = tws + i * (R0 - 1);
+        float2 a[H + 1], bq[H + 1];
+        const float2 x0 = cswap(p[0]);
+        float2 s0 = x0;
+        static_for<1, H + 1>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
+          const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
+          a[j] = cadd(s, t);
+          bq[j] = csub(s, t);
+          s0 = cadd(s0, a[j]);
+        });
+        auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };
+        emit(0, s0);
+        prime_outputs<R0, 1, H>(x0, a, bq, emit);
+      }
+    }
+  } else {
+    const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
+    if (tc < ncols) {
+#pragma unroll stage_unroll(R0)
+      for (int i = tb; i < m0; i += nb) {
+        const float2* p = tile + i * WP + tc;
+        float2 v[R0];
+#pragma unroll
+        for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
+        const float2* w = tws + i * (R0 - 1);
+#pragma unroll
+        for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+#pragma unroll
+        for (int q = 0; q < R0; ++q) v[q] = cswap(v[q]);
+        Dft<R0>::run(v);                                                 // |.| ignores the swap back
+#pragma unroll
+        for (int q = 0; q < R0; ++q) sink(i + q * m0, v[q]);
+      }
+    }
+  }
+}
+
 // Three CTAs per SM (<= 85 registers) pay off except for the radix-16 schedules, whose
 // butterflies need the registers (measured: 372 = 31*3*4 gains 8 %, 256 = 16*16 loses 12 %).
 template <class S> __host__ __device__ constexpr int cols_min_ctas() {
@@ -185,8 +291,8 @@ template <class S> __host__ __device__ constexpr int cols_min_ctas() {
     if (S::radix(j) == 16) return 2;
   return 3;
 }
-template <class S, bool MULTI>
-__global__ void __launch_bounds__(kThreads, cols_min_ctas<S>())
+template <class S, bool MULTI, int THREADS = kThreads, int MINCTAS = cols_min_ctas<S>(), bool SPLIT = true>
+__global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int D, int d0, int u0,
               int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
   GNSSACQ_DYN_SMEM(float2, tile);
@@ -194,7 +300,7 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
   const int N = pl.N, N2 = pl.N2;
   float* qs = reinterpret_cast<float*>(tile + N1 * WP);
   const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
-  constexpr int nb = kThreads / kTW;
+  constexpr int nb = THREADS / kTW;
   const int col0 = blockIdx.x * kTileW;
   const int ncols = imin(kTileW, N2 - col0);
   const int ul = blockIdx.y, u = u0 + ul;
@@ -203,7 +309,6 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
   float best = -1.f, sum = 0.f;
   int bestlag = 0x7fffffff;
   float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
-  const bool dump = qd != nullptr;
   const int lag0 = col0 + tc;
 
   for (int b = 0; b < B; ++b) {
@@ -225,73 +330,8 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
       }
       __syncthreads();
     }
-    inv_stages_smem<S, NS - 2, 1, WP, 1>(tile, ncols, pl.s1);
-    // ---- last inverse stage fused with |.|, the non-coherent sum and the peak search
-    constexpr int R0 = S::radix(0), m0 = S::stride(0);
-    auto sink = [&](int n1, float2 v) {
-      float acc = sqrt_fast(v.x * v.x + v.y * v.y);
-      if (MULTI) {
-        if (b > 0) acc += qs[n1 * WP + tc];
-        if (!last) { qs[n1 * WP + tc] = acc; return; }
-      }
-      sum += acc;
-      if (acc >= best) {                       // rare after the first few samples
-        const int lag = n1 * N2 + lag0;
-        if (lag < n_lags && (acc > best || lag < bestlag)) { best = acc; bestlag = lag; }
-      }
-      if (dump) qd[n1 * N2 + lag0] = acc * scale;
-    };
-    if constexpr (is_split_radix(R0)) {
-      // warp-pair butterfly (see stage_tile_split): both warps load, each emits half the outputs
-      constexpr int H = (R0 - 1) / 2, KA = (H + 1) / 2;
-      const int warp = threadIdx.x >> 5, role = warp & 1;
-      const int slot = (warp >> 1) * 2 + ((threadIdx.x >> 4) & 1);
-      constexpr int nslots = kThreads >> 5;
-      const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
-      for (int i = slot; i < m0; i += nslots) {
-        if (tc < ncols) {
-          const float2* p = tile + i * WP + tc;
-          const float2* w = tws + i * (R0 - 1);
-          float2 a[H + 1], bq[H + 1];
-          const float2 x0 = cswap(p[0]);
-          static_for<1, H + 1>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
-            const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
-            a[j] = cadd(s, t);
-            bq[j] = csub(s, t);
-          });
-          auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };      // |.| ignores the re/im swap
-          if (role == 0) {
-            float2 s0 = x0;
-            static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
-            emit(0, s0);
-            prime_outputs<R0, 1, KA>(x0, a, bq, emit);
-          } else {
-            prime_outputs<R0, KA + 1, H>(x0, a, bq, emit);
-          }
-        }
-      }
-    } else {
-      const float2* tws = pl.s1.tw + pl.s1.tws_off[0];
-      if (tc < ncols) {
-#pragma unroll stage_unroll(R0)
-        for (int i = tb; i < m0; i += nb) {
-          const float2* p = tile + i * WP + tc;
-          float2 v[R0];
-#pragma unroll
-          for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
-          const float2* w = tws + i * (R0 - 1);
-#pragma unroll
-          for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
-#pragma unroll
-          for (int q = 0; q < R0; ++q) v[q] = cswap(v[q]);
-          Dft<R0>::run(v);                                                 // |.| ignores the swap back
-#pragma unroll
-          for (int q = 0; q < R0; ++q) sink(i + q * m0, v[q]);
-        }
-      }
-    }
+    inv_stages_smem<S, NS - 2, 1, WP, 1, THREADS>(tile, ncols, pl.s1);
+    cols_last_stage<S, MULTI, THREADS, SPLIT>(tile, qs, pl, ncols, lag0, b, last, n_lags, scale, qd, best, bestlag, sum);
     if (MULTI && !last) __syncthreads();       // tile and q are reused by the next block
   }
   unsigned long long key = bestlag != 0x7fffffff ? pack_key(best * scale, bestlag) : 0ull;
@@ -452,49 +492,11 @@ using S250 = Sub<250, 10, 25>;
 using S248 = Sub<248, 31, 8>;
 using S496 = Sub<496, 31, 16>;
 
-typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
-typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
-
 template <class S> inline bool schedule_matches(const SubPlan& sp) {
   if (sp.F != S::F || sp.ns != S::NS) return false;
   for (int j = 0; j < S::NS; ++j)
     if (sp.radix[j] != S::radix(j) || sp.m[j] != S::stride(j)) return false;
   return true;
-}
-
-typedef void (*fwd_cols_fn)(DevPlan, const float2*, const float*, const double*, const float2*, int, int, float2*);
-typedef void (*fwd_rows_fn)(DevPlan, float2*);
-
-inline fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
-#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
-  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
-  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200) GNSSACQ_TRY(S248) GNSSACQ_TRY(S496) GNSSACQ_TRY(S186) GNSSACQ_TRY(S279)
-#undef GNSSACQ_TRY
-  return nullptr;
-}
-inline fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
-#define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
-  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S165)
-  GNSSACQ_TRY(S220)
-#undef GNSSACQ_TRY
-  return nullptr;
-}
-
-inline corr_rows_fn find_rows_kernel(const SubPlan& s2) {
-#define GNSSACQ_TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
-  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S512) GNSSACQ_TRY(S320) GNSSACQ_TRY(S186)
-  GNSSACQ_TRY(S279) GNSSACQ_TRY(S440) GNSSACQ_TRY(S250) GNSSACQ_TRY(S165)
-  GNSSACQ_TRY(S220)
-#undef GNSSACQ_TRY
-  return nullptr;
-}
-inline corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi) {
-#define GNSSACQ_TRY(S) if (schedule_matches<S>(s1)) return multi ? k_corr_cols_s<S, true> : k_corr_cols_s<S, false>;
-  GNSSACQ_TRY(S128) GNSSACQ_TRY(S256) GNSSACQ_TRY(S320) GNSSACQ_TRY(S165) GNSSACQ_TRY(S220)
-  GNSSACQ_TRY(S372) GNSSACQ_TRY(S200) GNSSACQ_TRY(S248) GNSSACQ_TRY(S496) GNSSACQ_TRY(S186) GNSSACQ_TRY(S279)
-#undef GNSSACQ_TRY
-  return nullptr;
 }
 
 }  // namespace acq

@@ -1,0 +1,93 @@
+// Instantiations of the plan-specialised kernels, split into parts (-DGNSSACQ_REG_PART=k) so
+// that nvcc compiles them in parallel. Schedules are exactly those fft_plan.h::make_subplan
+// emits for the FFT lengths GNSS receivers use; each is checked against the runtime plan.
+#include "registry.h"
+#include "kernels_small.cuh"
+
+namespace acq {
+
+#define COLS_LIST_0(T) T(S128) T(S256) T(S320) T(S165)
+#define COLS_LIST_1(T) T(S220) T(S372) T(S200) T(S248)
+#define COLS_LIST_2(T) T(S496) T(S186) T(S279)
+
+corr_cols_fn find_cols_part0(const SubPlan&, bool);
+corr_cols_fn find_cols_part1(const SubPlan&, bool);
+corr_cols_fn find_cols_part2(const SubPlan&, bool);
+corr_cols_fn find_cols_small_part0(const SubPlan&, bool);
+corr_cols_fn find_cols_small_part1(const SubPlan&, bool);
+corr_cols_fn find_cols_small_part2(const SubPlan&, bool);
+constexpr int kColsSmallThreads = 128;
+
+#if GNSSACQ_REG_PART == 0
+fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
+#define TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
+  TRY(S128) TRY(S256) TRY(S320) TRY(S165) TRY(S220) TRY(S372) TRY(S200) TRY(S248) TRY(S496) TRY(S186) TRY(S279)
+#undef TRY
+  return nullptr;
+}
+fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
+#define TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
+  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220)
+#undef TRY
+  return nullptr;
+}
+corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi) {
+  if (corr_cols_fn f = find_cols_part0(s1, multi)) return f;
+  if (corr_cols_fn f = find_cols_part1(s1, multi)) return f;
+  return find_cols_part2(s1, multi);
+}
+ColsSmall find_cols_small(const SubPlan& s1, bool multi) {
+  corr_cols_fn f = find_cols_small_part0(s1, multi);
+  if (!f) f = find_cols_small_part1(s1, multi);
+  if (!f) f = find_cols_small_part2(s1, multi);
+  return ColsSmall{f, f ? kColsSmallThreads : 0};
+}
+#elif GNSSACQ_REG_PART == 1
+corr_rows_fn find_rows_kernel(const SubPlan& s2) {
+#define TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
+  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220)
+#undef TRY
+  return nullptr;
+}
+// threads / CTAs per SM: enough registers for the widest in-register butterfly of the schedule.
+// Listed = measured faster than the 256-thread kernel on B200 (tools/bench_configs.py small_ctas=0..3,
+// profiles/README.md r02): 2-20 %; 256 = 16*16 lost 2-7 % and stays on the 256-thread kernel.
+RowsSmall find_rows_small(const SubPlan& s2) {
+  static_assert(kRowsSmallTile == kRowsTile8, "row tile");
+#define TRY(S, T, C) if (schedule_matches<S>(s2)) return RowsSmall{k_corr_rows_t<S, T, C>, T, rows_t_smem<S>()};
+  TRY(S440, 160, 5) TRY(S128, 128, 6) TRY(S512, 128, 6) TRY(S320, 128, 6) TRY(S220, 128, 4) TRY(S250, 128, 4)
+#undef TRY
+  return RowsSmall{nullptr, 0, 0};
+}
+#elif GNSSACQ_REG_PART >= 2 && GNSSACQ_REG_PART <= 4
+#define TRY(S) if (schedule_matches<S>(s1)) return multi ? k_corr_cols_s<S, true> : k_corr_cols_s<S, false>;
+#if GNSSACQ_REG_PART == 2
+corr_cols_fn find_cols_part0(const SubPlan& s1, bool multi) { COLS_LIST_0(TRY) return nullptr; }
+#elif GNSSACQ_REG_PART == 3
+corr_cols_fn find_cols_part1(const SubPlan& s1, bool multi) { COLS_LIST_1(TRY) return nullptr; }
+#else
+corr_cols_fn find_cols_part2(const SubPlan& s1, bool multi) { COLS_LIST_2(TRY) return nullptr; }
+#endif
+#undef TRY
+#elif GNSSACQ_REG_PART >= 5 && GNSSACQ_REG_PART <= 7
+// Listed = measured faster than the 256-thread kernel (same measurements): every schedule with a
+// radix-31 stage (3-10 %), 128 = 8*16 (17 %), 200 = 10*20 (2 %), 256 = 16*16 for one block only
+// (+9 %; -5 % with the non-coherent accumulator in shared memory). 320 = 5*8*8 lost 8 %.
+#define TRY(S) if (schedule_matches<S>(s1)) return multi ? k_corr_cols_s<S, true, kColsSmallThreads, 4, false> : k_corr_cols_s<S, false, kColsSmallThreads, 4, false>;
+#if GNSSACQ_REG_PART == 5
+corr_cols_fn find_cols_small_part0(const SubPlan& s1, bool multi) {
+  TRY(S128)
+  if (!multi && schedule_matches<S256>(s1)) return k_corr_cols_s<S256, false, kColsSmallThreads, 4, false>;
+  return nullptr;
+}
+#elif GNSSACQ_REG_PART == 6
+corr_cols_fn find_cols_small_part1(const SubPlan& s1, bool multi) { TRY(S372) TRY(S200) TRY(S248) return nullptr; }
+#else
+corr_cols_fn find_cols_small_part2(const SubPlan& s1, bool multi) { COLS_LIST_2(TRY) return nullptr; }
+#endif
+#undef TRY
+#else
+#error "GNSSACQ_REG_PART must be 0..7"
+#endif
+
+}  // namespace acq

@@ -1,0 +1,29 @@
+// Lookup of the plan-specialised kernels by radix schedule. The template instantiations behind
+// these functions are compiled in separate translation units (registry.cu, one part per nvcc
+// invocation, see __graft_entry__.build) so that the library builds in parallel.
+#pragma once
+#include "fft_core.cuh"
+#include "kernels.cuh"
+
+namespace acq {
+
+typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
+typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
+typedef void (*fwd_cols_fn)(DevPlan, const float2*, const float*, const double*, const float2*, int, int, float2*);
+typedef void (*fwd_rows_fn)(DevPlan, float2*);
+
+// 256-thread kernels (kernels_spec.cuh); nullptr when the schedule has no specialisation
+fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src);
+fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2);
+corr_rows_fn find_rows_kernel(const SubPlan& s2);
+corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi);
+
+// small-CTA kernels (kernels_small.cuh): rows grid = (ceil(N1/8), B, units) with `smem` bytes,
+// columns grid and shared memory as the 256-thread kernel
+struct RowsSmall { corr_rows_fn fn; int threads; size_t smem; };
+struct ColsSmall { corr_cols_fn fn; int threads; };
+constexpr int kRowsSmallTile = 8;
+RowsSmall find_rows_small(const SubPlan& s2);
+ColsSmall find_cols_small(const SubPlan& s1, bool multi);
+
+}  // namespace acq

@@ -46,6 +46,8 @@ def _declare(lib):
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
         'gnssacq_mix': [p, p, i64, dbl, dbl],
         'gnssacq_preprocess': [p, p, i64, dbl, dbl, p, i32, dbl, i64, p],
+        'gnssacq_set_replicas_from_chips': [p, p, i32, i32, i32, i32, dbl, dbl, i32, dbl],
+        'gnssacq_correlate_bank': [p, p, i32, dbl, i32, i32, i32, p, i32, dbl, p],
         'gnssacq_plan_info': [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         'gnssacq_synchronize': [p],
         'gnssacq_kernel_variant': [p],
@@ -135,6 +137,32 @@ class Engine:
             rep = np.ascontiguousarray(rep, dtype=np.float32)
             self._check(self._lib.gnssacq_set_replicas(self._h, _ptr(rep), rep.shape[0], rep.shape[1]))
         self.R, self.N = rep.shape
+
+    def set_replicas_from_chips(self, chips01, n, N, incr, boc=False, chips=0, frac=0):
+        """Build the R replicas on the device from R x L chip tables (0/1): what
+        `<sig>.code(prn, chips, frac, incr, n)` [* nco.boc11(chips, frac, incr, n)] followed by
+        N - n zeros would give (acquire-gps-l1.py:22-24, acquire-gps-l1cd.py:22-26)."""
+        c = np.ascontiguousarray(chips01, dtype=np.int8)
+        if c.ndim != 2:
+            raise ValueError('chips must be R x L')
+        R, L = c.shape
+        base = float((chips % L) + frac)              # gnsstools/gps/ca.py:108, float64 like numpy
+        base2 = float((chips % 2) + frac)             # gnsstools/nco.py:15
+        self._check(self._lib.gnssacq_set_replicas_from_chips(self._h, _ptr(c), R, L, int(n), int(N), base, float(incr),
+                                                              1 if boc else 0, base2))
+        self.R, self.N = R, int(N)
+
+    def correlate_bank(self, chips01, nco_freq, n, n_blocks, block_stride, base, incr):
+        """out[h, b] = sum_i x[b*stride+i] * nco(nco_freq,0,n)[i] * (1-2*chips01[floor(base[h,b]+incr*i) mod L])
+        on the resident capture; base = (chips % L) + frac per (hypothesis, block), float64."""
+        c = np.ascontiguousarray(chips01, dtype=np.int8).ravel()
+        base = np.ascontiguousarray(base, dtype=np.float64)
+        if base.ndim != 2 or base.shape[1] != n_blocks:
+            raise ValueError('base must be H x n_blocks')
+        out = np.empty(base.shape, dtype=np.complex128)
+        self._check(self._lib.gnssacq_correlate_bank(self._h, _ptr(c), c.size, float(nco_freq), int(n), int(n_blocks),
+                                                     int(block_stride), _ptr(base), base.shape[0], float(incr), _ptr(out)))
+        return out
 
     def set_replicas_i8_device(self, device_ptr, R, N):
         self._check(self._lib.gnssacq_set_replicas_i8_device(self._h, C.c_void_p(int(device_ptr)), int(R), int(N)))

@@ -5,8 +5,9 @@ worker() / mp.Pool fan-out that every reference acquire-*.py script carries
 ``acquire(signal, x, keys, doppler_search, ms)`` runs every (PRN x Doppler bin x block) of a
 script's search in one call into libgnssacq.so; ``search(signal, x, key, doppler_search, ms)``
 keeps the reference's per-PRN signature and return value ``(metric, code_chips, doppler_hz)``.
-All arithmetic of the search runs on the device; this module only prepares the replicas
-(host, once per PRN, as in the reference) and converts the returned lag index to chips.
+All arithmetic of the search runs on the device, including the replica set-up (resampled code,
+BOC(1,1), zero half, FFT) from the chip tables; this module only hands over the tables and
+converts the returned lag index to chips.
 """
 
 import importlib
@@ -112,6 +113,30 @@ def replica(sig, key):
     return out
 
 
+_chip_cache = {}
+
+
+def chip_table(sig, key):
+    """0/1 chips of one code period, read through the module's public code() at one sample per
+    chip (every generator names its table accessor differently; code() is common to all)."""
+    ck = (sig.module, None if sig.fdma else key)
+    if ck not in _chip_cache:
+        mod = code_module(sig)
+        L = mod.code_length
+        c = mod.code(0, 0, 1.0, L) if sig.fdma else mod.code(key, 0, 0, 1.0, L)
+        _chip_cache[ck] = ((1.0 - c) * 0.5).astype(np.int8)
+    return _chip_cache[ck]
+
+
+def set_replicas(eng, sig, keys):
+    """Replicas of `keys` built on the device from the chip tables (gnssacq_set_replicas_from_chips):
+    resampling, BOC(1,1) and zero padding of replica() without the per-sample host work and upload."""
+    mod = code_module(sig)
+    incr = float(sig.periods * mod.code_length) / sig.n
+    chips = np.stack([chip_table(sig, k) for k in keys])
+    eng.set_replicas_from_chips(chips, sig.n, sig.N, incr, boc=sig.boc)
+
+
 def doppler_bins(doppler_search):
     lo, hi, step = doppler_search
     return np.arange(lo, hi, step)          # max excluded (acquire-gps-l1.py:26)
@@ -156,13 +181,13 @@ def acquire(signal, x, keys, doppler_search, ms, engine=None, lag_limit=0, block
         eng.set_signal(np.ascontiguousarray(x[:need], dtype=np.complex64))
     out = []
     if sig.fdma:
-        eng.set_replicas(replica(sig, None)[None, :])
+        set_replicas(eng, sig, [None])
         for chan in keys:
             f = -(sig.carrier_step * chan + bins) / sig.fs          # acquire-glonass-l1.py:28
             metric, lag, dbin = eng.search(f, sig.n, B, sig.normalize, lag_limit)
             out.append(_finish(sig, L, bins, metric[0], lag[0], dbin[0]))
         return out
-    eng.set_replicas(np.stack([replica(sig, k) for k in keys]))
+    set_replicas(eng, sig, keys)
     f = -bins / sig.fs                                              # acquire-gps-l1.py:28
     metric, lag, dbin = eng.search(f, sig.n, B, sig.normalize, lag_limit)
     return [_finish(sig, L, bins, metric[i], lag[i], dbin[i]) for i in range(len(keys))]

@@ -115,6 +115,29 @@ int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq_int8, int64_t n_samples, d
                        const double* fir, int32_t ntaps, double step, int64_t n_out, double* out_c128);
 
 /* Introspection for tests and the benchmark. */
+/* Replica set-up on the device: what `<sig>.code(prn,0,0,incr,n)`
+ * (gnsstools/gps/ca.py:106-112), optionally times nco.boc11(0,0,incr,n) (gnsstools/nco.py:12-19),
+ * optionally followed by n zeros, hands to fft.fft() in every search()
+ * (acquire-gps-l1.py:22-24, acquire-gps-l1cd.py:22-26, acquire-gps-l5i.py:22-24) — built from
+ * the 0/1 chip tables instead of being resampled on the host and uploaded sample by sample.
+ * chips01: R tables of L chips (values 0/1). Replica r, sample i < n takes chip
+ * floor(base + incr*i) mod L with base = (chips % L) + frac formed by the caller in float64
+ * (0.0 for the acquisition scripts); boc != 0 multiplies by the BOC(1,1) square wave with
+ * base2 = (chips % 2) + frac; samples n..N-1 are zero. Then as gnssacq_set_replicas. */
+int gnssacq_set_replicas_from_chips(gnssacq_t* h, const int8_t* chips01, int32_t R, int32_t L, int32_t n, int32_t N,
+                                    double base, double incr, int32_t boc, double base2);
+
+/* Time-domain correlator bank for the serial long-code acquisitions:
+ * acquire-gps-l2cl.py:18-33, acquire-glonass-l1-p.py:14-32, acquire-glonass-l2-p.py:14-32.
+ * For every hypothesis h < H and block b < n_blocks:
+ *   out[h][b] = sum_{i<n} x[b*block_stride + i] * nco(nco_freq, 0, n)[i] * (1 - 2*chips01[idx])
+ *   idx = floor(base[h*n_blocks + b] + incr*i) mod L,   base = (chips % L) + frac (caller, float64)
+ * on the capture given to gnssacq_set_signal. out_c128: H*n_blocks complex128, interleaved
+ * re,im (the reference then forms q[h] = sum_b |out[h][b]| and keeps the first maximum). */
+int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, double nco_freq, int32_t n,
+                           int32_t n_blocks, int32_t block_stride, const double* base, int32_t H, double incr,
+                           double* out_c128);
+
 int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
 /* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =
@@ -127,7 +150,10 @@ int gnssacq_synchronize(gnssacq_t* h);
  * runtime-planned kernels. Both produce the same results to rounding.
  * "overlap_chunks" (default 1): large plans alternate their unit chunks over two internal
  * streams so the rows kernel of one chunk overlaps the columns kernel of the other; 0 runs
- * every kernel back to back on the handle's stream (what per-kernel stage times need). */
+ * every kernel back to back on the handle's stream (what per-kernel stage times need).
+ * "small_ctas" (default 3): bit 0 = 8-row / 128-160-thread rows kernel, bit 1 = 128-thread
+ * columns kernel with the radix-31 butterfly in one thread (4-7 CTAs per SM instead of 2-3;
+ * bit-identical results); 0 = the 256-thread kernels. */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Tuning: force the stage radices (forward order) of the length-N1 (which = 1) or length-N2
  * (which = 2) tile transform; ignored when their product does not match; n = 0 restores the

@@ -182,3 +182,49 @@ def search_script(script, x, chip_bits, key, doppler_search, ms, **kw):
     return search(x, chip_bits, s['fs'], s['n'], doppler_search, s['blocks'](ms),
                   pad=s['pad'], boc=s['boc'], normalize=s['normalize'],
                   mod_L=s['mod_L'], carrier_hz=carrier, **kw)
+
+
+# --------------------------------------------------------------------------- serial long-code searches
+# (the time-domain correlator bank behind gnssacq_correlate_bank)
+
+def search_l2cl(x, chip_bits, fs, doppler, l2cm_code_phase, ms, hypotheses=75):
+    """reference acquire-gps-l2cl.py:18-33: 75 hypotheses of which 10230-chip L2CM period the
+    767250-chip L2CL code is in, 20 ms blocks, q = sum_block |sum(x*c*w)|, first maximum by strict '>'."""
+    blocks = ms // 20
+    n = int(fs * 0.020)
+    w = nco(-doppler / fs, 0, n)
+    incr = 511500 / fs                                   # l2cl.chip_rate
+    m_metric, m_k = 0, 0
+    for k in range(hypotheses):
+        q = 0
+        for block in range(blocks):
+            c = resample_code(chip_bits, (k + block) * 10230 + l2cm_code_phase, 0, incr, n)
+            p = x[n * block:n * (block + 1)] * c * w
+            q = q + np.absolute(np.sum(p))
+        if q > m_metric:
+            m_metric = q
+            m_k = k
+    return m_metric, m_k
+
+
+def search_glonass_p(x, chip_bits, fs, carrier_step, chan, doppler, ca_code_phase, ms, hypotheses=1000):
+    """reference acquire-glonass-l1-p.py:14-32 (carrier_step 562500) and acquire-glonass-l2-p.py:14-32
+    (437500): 1000 hypotheses of which C/A period (5110 P chips) the 5110000-chip P code is in, 4 ms
+    blocks; the code phase advances by the float accumulation cp += n*incr and enters code() as `frac`."""
+    blocks = ms // 4
+    n = int(fs * 0.004)
+    w = nco(-(carrier_step * chan + doppler) / fs, 0, n)
+    m_metric, m_k = 0, 0
+    for k in range(hypotheses):
+        q = 0
+        cp = 5110 * k + 10 * ca_code_phase
+        for block in range(blocks):
+            incr = 5110000.0 / fs
+            c = resample_code(chip_bits, 0, cp, incr, n)
+            xp = x[n * block:n * (block + 1)] * c * w
+            q = q + np.absolute(np.sum(xp))
+            cp += n * incr
+        if q > m_metric:
+            m_metric = q
+            m_k = k
+    return m_metric, m_k

@@ -33,6 +33,8 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct float2 { float x, y; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };

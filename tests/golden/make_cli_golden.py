@@ -27,3 +27,18 @@ for case in synth_files.CLI_CASES:
     out[case] = r.stdout.splitlines()
     print(case, out[case], flush=True)
 json.dump(out, open(os.path.join(HERE, 'cli_golden.json'), 'w'), indent=1)
+
+# serial long-code acquisitions (acquire-gps-l2cl.py, acquire-glonass-l{1,2}-p.py)
+out = {}
+for case in synth_files.SERIAL_CASES:
+    with tempfile.NamedTemporaryFile(suffix='.iq', delete=False) as f:
+        f.write(synth_files.recording_serial(case))
+        path = f.name
+    script, args = synth_files.command_serial(case, path)
+    r = subprocess.run([sys.executable, '-W', 'ignore', os.path.join(REF, 'acquire-%s.py' % script)] + args,
+                       capture_output=True, text=True, cwd=REF)
+    os.unlink(path)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out[case] = r.stdout.splitlines()
+    print(case, out[case], flush=True)
+json.dump(out, open(os.path.join(HERE, 'cli_serial_golden.json'), 'w'), indent=1)

@@ -49,3 +49,38 @@ def recording(case):
 def command(case, path):
     script, fs, coffset, opts, _, _, _ = CLI_CASES[case]
     return script, opts + [path, repr(fs), repr(coffset)]
+
+
+# Serial long-code acquisitions (acquire-gps-l2cl.py, acquire-glonass-l{1,2}-p.py):
+# name -> (script, fs_file, coffset, options, ms, key (prn / channel), doppler, coarse phase, true k, amp, seed)
+SERIAL_CASES = {
+    'gps-l2cl': ('gps-l2cl', 2400000.0, -100000.0, ['--time', '40'], 40, 3, 431.0, 8317.2, 17, 2.0, 31),
+    'glonass-l1-p': ('glonass-l1-p', 6000000.0, 250000.0, ['--time', '8'], 8, -2, 310.0, 278.6, 421, 2.0, 32),
+    'glonass-l2-p': ('glonass-l2-p', 6000000.0, -125000.0, ['--time', '12'], 12, 3, -220.0, 33.4, 77, 2.0, 33),
+}
+
+
+def recording_serial(case):
+    """int8 interleaved I/Q bytes of (ms+5) ms with the long code planted at hypothesis `true k`."""
+    script, fs, coffset, _, ms, key, doppler, phase, k_true, amp, seed = SERIAL_CASES[case]
+    rng = np.random.default_rng(seed)
+    n = int(fs * 0.001 * (ms + 5))
+    t = np.arange(n)
+    if script == 'gps-l2cl':
+        import gnsstools.gps.l2cl as l2cl
+        c = resample(l2cl.l2cl_code(key), k_true * 10230 + phase, 0, l2cl.chip_rate / fs, n)
+        fc = coffset + doppler
+    else:
+        import gnsstools.glonass.p as p
+        c = resample(p.p_code(), 5110 * k_true + 10 * phase, 0, 5110000.0 / fs, n)
+        fc = coffset + doppler + (562500 if script == 'glonass-l1-p' else 437500) * key
+    x = amp * c * np.exp(2j * np.pi * fc * t / fs) + rng.normal(0, 8, n) + 1j * rng.normal(0, 8, n)
+    iq = np.empty(2 * n, dtype=np.int8)
+    iq[0::2] = np.clip(np.round(x.real), -127, 127)
+    iq[1::2] = np.clip(np.round(x.imag), -127, 127)
+    return iq.tobytes()
+
+
+def command_serial(case, path):
+    script, fs, coffset, opts, _, key, doppler, phase, _, _, _ = SERIAL_CASES[case]
+    return script, opts + [path, repr(fs), repr(coffset), str(key), repr(doppler), repr(phase)]

@@ -69,3 +69,46 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, '_default_engine', None)
     with pytest.raises(_native.NativeError):
         _native.default_engine()
+
+
+# --------------------------------------------------------------------------- serial long-code acquisitions
+GOLD_SERIAL = json.load(open(os.path.join(HERE, 'golden', 'cli_serial_golden.json')))
+
+
+def compare_serial(got_lines, want_lines):
+    """'%f %f' % (code_phase, metric): the code phase (hypothesis index) is exact, the metric within 1e-4."""
+    assert len(got_lines) == len(want_lines) == 1
+    g, w = got_lines[0].split(), want_lines[0].split()
+    assert g[0] == w[0], (got_lines, want_lines)
+    assert abs(float(g[1]) - float(w[1])) <= 1e-4 * float(w[1]), (got_lines, want_lines)
+
+
+def test_l2cl_cli_on_emulated_kernels(tmp_path, monkeypatch, capsys):
+    """acquire-gps-l2cl.py end to end, correlator bank compiled for the host (test harness)."""
+    import importlib.util
+    import emu_util
+    from gnsstools import _native
+    eng = emu_util.emu_engine()
+    monkeypatch.setattr(_native, '_default_engine', eng)
+    p = tmp_path / 'l2cl.iq'
+    p.write_bytes(synth_files.recording_serial('gps-l2cl'))
+    script, args = synth_files.command_serial('gps-l2cl', str(p))
+    spec = importlib.util.spec_from_file_location('acquire_gps_l2cl', os.path.join(PKG, 'acquire-%s.py' % script))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main(args)
+    compare_serial(capsys.readouterr().out.splitlines(), GOLD_SERIAL['gps-l2cl'])
+    monkeypatch.setattr(_native, '_default_engine', None)
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', sorted(synth_files.SERIAL_CASES))
+def test_serial_scripts_match_reference_stdout(case, tmp_path):
+    p = tmp_path / (case + '.iq')
+    p.write_bytes(synth_files.recording_serial(case))
+    script, args = synth_files.command_serial(case, str(p))
+    r = subprocess.run([sys.executable, os.path.join(PKG, 'acquire-%s.py' % script)] + args,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    compare_serial(r.stdout.splitlines(), GOLD_SERIAL[case])

@@ -100,3 +100,66 @@ def test_errors(eng):
         eng.search(np.array([0.0]), 64, 2, False)          # capture too short
     with pytest.raises(ValueError):
         eng.set_replicas(np.ones((1, 2 * 37), np.float32))  # prime factor 37 unsupported
+
+
+# --------------------------------------------------------------------------- replica builder / correlator bank
+@pytest.mark.parametrize('module,key,n,pad,boc', [('gps.ca', 5, 2046, False, False), ('galileo.e1b', 11, 4092, True, True),
+                                                  ('gps.l5i', 3, 2500, True, False), ('glonass.ca', None, 1000, False, False)])
+def test_replica_builder_equals_host_replica(eng, module, key, n, pad, boc):
+    """gnssacq_set_replicas_from_chips builds exactly the samples acquire.replica() builds on the host
+    (reference <sig>.code x nco.boc11, zero half): identical replicas -> bit-identical q grids."""
+    from gnsstools import acquire
+    sig = acquire.Signal(module, 1.0e6, n, lambda ms: ms, pad=pad, boc=boc, fdma=key is None)
+    rng = np.random.default_rng(3)
+    x = (rng.normal(0, 8, 3 * n) + 1j * rng.normal(0, 8, 3 * n)).astype(np.complex64)
+    f = np.array([0.0, 1.5e-4])
+    eng.set_signal(x)
+    eng.set_replicas(acquire.replica(sig, key)[None, :])
+    a = eng.search(f, n, 1, False, dump=True)
+    acquire.set_replicas(eng, sig, [key])
+    b = eng.search(f, n, 1, False, dump=True)
+    assert np.array_equal(a[3], b[3]) and a[1][0] == b[1][0] and a[0][0] == b[0][0]
+
+
+def test_correlator_bank_matches_numpy(eng):
+    rng = np.random.default_rng(4)
+    L, n, B, H = 5000, 3000, 3, 7
+    chips = rng.integers(0, 2, L).astype(np.int8)
+    x = (rng.normal(0, 8, B * n) + 1j * rng.normal(0, 8, B * n)).astype(np.complex64)
+    f, incr = -1.234e-3, 0.731
+    base = rng.uniform(0, L, (H, B))
+    base[0, 0] = L - 0.25                      # wraps inside the block
+    eng.set_signal(x)
+    got = eng.correlate_bank(chips, f, n, B, n, base, incr)
+    w = orc.nco(f, 0, n)
+    for h in range(H):
+        for b in range(B):
+            c = orc.resample_code(chips, 0, base[h, b], incr, n)
+            want = np.sum(x[b * n:(b + 1) * n].astype(np.complex128) * c * w)
+            assert abs(got[h, b] - want) <= 1e-5 * np.sum(np.abs(x[b * n:(b + 1) * n])), (h, b)
+
+
+def test_serial_searches_match_oracle(eng):
+    """acquire-gps-l2cl.py / acquire-glonass-l1-p.py search() through the correlator bank."""
+    from gnsstools import acquire_serial
+    import gnsstools.gps.l2cl as l2cl
+    import gnsstools.glonass.p as gp
+    rng = np.random.default_rng(6)
+    fs, ms, prn, doppler, cm = 0.3e6, 40, 3, 431.0, 8317.2
+    nx = int(fs * 0.001 * (ms + 5))
+    t = np.arange(nx)
+    x = rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)
+    x += 3.0 * orc.resample_code(l2cl.l2cl_code(prn), 4 * 10230 + cm, 0, 511500.0 / fs, nx) * np.exp(2j * np.pi * doppler * t / fs)
+    x = x.astype(np.complex64)
+    got = acquire_serial.search_l2cl(x, prn, doppler, cm, ms, fs, engine=eng, hypotheses=9)
+    want = orc.search_l2cl(x, l2cl.l2cl_code(prn), fs, doppler, cm, ms, hypotheses=9)
+    assert got[1] == want[1] == 4 and abs(got[0] - want[0]) <= 1e-4 * want[0]
+    fs, ms, chan, doppler, ca = 1.0e6, 8, -2, 310.0, 278.6
+    nx = int(fs * 0.001 * (ms + 5))
+    t = np.arange(nx)
+    x = rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)
+    x += 3.0 * orc.resample_code(gp.p_code(), 5110 * 6 + 10 * ca, 0, 5110000.0 / fs, nx) * np.exp(2j * np.pi * (562500 * chan + doppler) * t / fs)
+    x = x.astype(np.complex64)
+    got = acquire_serial.search_glonass_p(x, chan, doppler, ca, ms, fs, 562500, engine=eng, hypotheses=10)
+    want = orc.search_glonass_p(x, gp.p_code(), fs, 562500, chan, doppler, ca, ms, hypotheses=10)
+    assert got[1] == want[1] == 6 and abs(got[0] - want[0]) <= 1e-4 * want[0]

@@ -171,3 +171,67 @@ def test_full_size_config2_property(eng):
     assert np.array_equal(np.where(take1, m1, m0), mf)
     assert np.array_equal(np.where(take1, l1, l0), lf)
     assert np.array_equal(np.where(take1, d1 + 40, d0), df)
+
+
+# --------------------------------------------------------------------------- replica builder / correlator bank
+@pytest.mark.parametrize('signal,keys', [('gps-l1', [1, 17, 32]), ('gps-l1cd', [4]), ('galileo-e1b', [11, 12]),
+                                         ('gps-l5i', [2]), ('glonass-l1', [None]), ('beidou-b2ap', [9])])
+def test_replica_builder_equals_host_replica(eng, signal, keys):
+    """gnssacq_set_replicas_from_chips (device: resample + BOC(1,1) + zero half) gives the samples
+    of the host construction acquire.replica() (reference <sig>.code x nco.boc11): the q grids of
+    the two set-ups are bit-identical."""
+    from gnsstools import acquire
+    sig = acquire.SIGNALS[signal]
+    rng = np.random.default_rng(3)
+    x = (rng.normal(0, 8, sig.n + sig.N) + 1j * rng.normal(0, 8, sig.n + sig.N)).astype(np.complex64)
+    f = np.array([0.0, 1.5e-5])
+    eng.set_signal(x)
+    eng.set_replicas(np.stack([acquire.replica(sig, k) for k in keys]))
+    a = eng.search(f, sig.n, 1, sig.normalize, dump=True)
+    acquire.set_replicas(eng, sig, keys)
+    b = eng.search(f, sig.n, 1, sig.normalize, dump=True)
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+def test_correlator_bank_matches_numpy(eng):
+    rng = np.random.default_rng(4)
+    L, n, B, H = 767250, 81920, 2, 40
+    chips = rng.integers(0, 2, L).astype(np.int8)
+    x = (rng.normal(0, 8, B * n) + 1j * rng.normal(0, 8, B * n)).astype(np.complex64)
+    f, incr = -1.234e-3, 0.12488
+    base = rng.uniform(0, L, (H, B))
+    base[0, 0] = L - 0.25                      # wraps inside the block
+    eng.set_signal(x)
+    got = eng.correlate_bank(chips, f, n, B, n, base, incr)
+    w = orc.nco(f, 0, n)
+    for h in range(H):
+        for b in range(B):
+            c = orc.resample_code(chips, 0, base[h, b], incr, n)
+            xb = x[b * n:(b + 1) * n].astype(np.complex128)
+            assert abs(got[h, b] - np.sum(xb * c * w)) <= 1e-6 * np.sum(np.abs(xb)), (h, b)
+
+
+def test_serial_searches_match_oracle(eng):
+    """search() of acquire-gps-l2cl.py and acquire-glonass-l1-p.py at their full hypothesis counts."""
+    from gnsstools import acquire_serial
+    import gnsstools.gps.l2cl as l2cl
+    import gnsstools.glonass.p as gp
+    rng = np.random.default_rng(6)
+    fs, ms, prn, doppler, cm = 4.096e6, 40, 3, 431.0, 8317.2
+    nx = int(fs * 0.001 * (ms + 5))
+    t = np.arange(nx)
+    x = rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)
+    x += 1.0 * orc.resample_code(l2cl.l2cl_code(prn), 44 * 10230 + cm, 0, 511500.0 / fs, nx) * np.exp(2j * np.pi * doppler * t / fs)
+    x = x.astype(np.complex64)
+    got = acquire_serial.search_l2cl(x, prn, doppler, cm, ms, fs, engine=eng)
+    want = orc.search_l2cl(x, l2cl.l2cl_code(prn), fs, doppler, cm, ms)
+    assert got[1] == want[1] == 44 and abs(got[0] - want[0]) <= METRIC_RTOL * want[0]
+    fs, ms, chan, doppler, ca = 6.0e6, 8, -2, 310.0, 278.6
+    nx = int(fs * 0.001 * (ms + 5))
+    t = np.arange(nx)
+    x = rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)
+    x += 1.5 * orc.resample_code(gp.p_code(), 5110 * 612 + 10 * ca, 0, 5110000.0 / fs, nx) * np.exp(2j * np.pi * (562500 * chan + doppler) * t / fs)
+    x = x.astype(np.complex64)
+    got = acquire_serial.search_glonass_p(x, chan, doppler, ca, ms, fs, 562500, engine=eng)
+    want = orc.search_glonass_p(x, gp.p_code(), fs, 562500, chan, doppler, ca, ms)
+    assert got[1] == want[1] == 612 and abs(got[0] - want[0]) <= METRIC_RTOL * want[0]

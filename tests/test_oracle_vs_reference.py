@@ -94,3 +94,41 @@ def test_oracle_helpers_match_reference():
         orc.mix(a, f, p)
         rnco.mix(b, f, p)
         assert np.array_equal(a, b)
+
+
+# --------------------------------------------------------------------------- serial long-code searches
+def _serial_capture(chips, L, chip_rate, fs, n_total, phase_chips, fd, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0, 8, n_total) + 1j * rng.normal(0, 8, n_total)
+    t = np.arange(n_total)
+    c = orc.resample_code(chips, phase_chips, 0, chip_rate / fs, n_total)
+    x += 2.0 * c * np.exp(2j * np.pi * fd * t / fs)
+    return x.astype(np.complex64)
+
+
+def test_oracle_matches_reference_l2cl_search():
+    """acquire-gps-l2cl.py search() (75 hypotheses, hard-coded) at a small sample rate."""
+    ref_search, ns = ref_lift.lift_search('gps-l2cl')
+    l2cl = ns['l2cl']
+    fs, ms, prn, doppler, cm_phase = 1.2e6, 40, 3, 431.0, 8317.2
+    ns['fs'] = fs
+    chips = np.asarray(l2cl.l2cl_code(prn))
+    x = _serial_capture(chips, 767250, 511500.0, fs, int(fs * 0.001 * (ms + 5)), 17 * 10230 + cm_phase, doppler, seed=11)
+    want = ref_search(x, prn, doppler, cm_phase, ms)
+    got = orc.search_l2cl(x, chips, fs, doppler, cm_phase, ms)
+    assert got == tuple(want) and got[1] == 17, (got, want)
+
+
+@pytest.mark.parametrize('band,step', [('l1', 562500), ('l2', 437500)])
+def test_oracle_matches_reference_glonass_p_search(band, step):
+    """acquire-glonass-l{1,2}-p.py search() (1000 hypotheses, hard-coded) at a small sample rate."""
+    ref_search, ns = ref_lift.lift_search('glonass-%s-p' % band)
+    p = ns['p']
+    fs, ms, chan, doppler, ca_phase = 5.0e6, 8, -2, 310.0, 278.6
+    ns['fs'] = fs
+    chips = np.asarray(p.p_code())
+    x = _serial_capture(chips, 5110000, 5110000.0, fs, int(fs * 0.001 * (ms + 5)), 5110 * 421 + 10 * ca_phase,
+                        step * chan + doppler, seed=12)
+    want = ref_search(x, chan, doppler, ca_phase, ms)
+    got = orc.search_glonass_p(x, chips, fs, step, chan, doppler, ca_phase, ms)
+    assert got == tuple(want) and got[1] == 421, (got, want)

@@ -35,7 +35,11 @@ stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
 rng = np.random.default_rng(0)
-only = sys.argv[1:] 
+only = [a for a in sys.argv[1:] if '=' not in a]
+for a in sys.argv[1:]:
+    if '=' in a:                      # engine option name=value (A/B measurements)
+        k, v = a.split('=')
+        eng.set_option(k, int(v))
 for name, n, pad, R, D, B, norm in CASES:
     if only and not any(o in name for o in only):
         continue
