@@ -31,6 +31,7 @@ struct SubPlan {
   int tws_off[kMaxStages];  // stage j twiddles, butterfly-major: tw[tws_off[j] + i*(R-1) + (q-1)]
                             //   = exp(-2*pi*i * q*i / (R*m)),  i < m, 1 <= q < R   (0 if m == 1)
   int tws0_t_off;           // stage 0 again, q-major: tw[tws0_t_off + (q-1)*m + i]
+  int pfa;                  // 1: prime-factor transform, the stage twiddles are not applied (fft_plan.h)
 };
 
 // ---------------------------------------------------------------- complex helpers
@@ -354,7 +355,8 @@ __device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, 
   });
 }
 
-template <int P, bool INV, int ES = 0, int CS = 1>
+// NOTW: prime-factor transform, no stage twiddles.
+template <int P, bool INV, int ES = 0, int CS = 1, bool NOTW = false>
 __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F, int m,
                                                  const float2* __restrict__ tw, int WPrt = 0) {
   const int WP = ES ? ES : WPrt;             // element stride: compile-time when ES != 0
@@ -382,7 +384,7 @@ __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F,
     auto in = [&](int q) -> float2 {
       float2 v = p[q * estride];
       if (INV) {
-        if (m > 1 && q > 0) v = cmulc(v, __ldg(&tw[q * twi]));
+        if (!NOTW && m > 1 && q > 0) v = cmulc(v, __ldg(&tw[q * twi]));
         v = cswap(v);
       }
       return v;
@@ -400,7 +402,7 @@ __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F,
     if (active) {
       auto emit = [&](int q, float2 v) {
         if (INV) v = cswap(v);
-        else if (m > 1 && q > 0) v = cmul(v, __ldg(&tw[q * twi]));
+        else if (!NOTW && m > 1 && q > 0) v = cmul(v, __ldg(&tw[q * twi]));
         p[q * estride] = v;
       };
       if (role == 0) {

@@ -20,7 +20,40 @@ struct HostSubPlan {
   int tws0_t_off = 0;                // offset of stage 0's q-major copy
   std::vector<int> pos_of_freq;      // position of frequency k after the forward transform
   std::vector<int> freq_of_pos;
+  // Prime-factor (Good-Thomas) form: when the radices are pairwise coprime the transform is a
+  // plain multi-dimensional DFT over the digits of the tile position — no stage twiddles — at the
+  // price of index maps on both sides: position p = sum_j d_j m_j holds time sample
+  // n = sum_j d_j (F/R_j) mod F before, and frequency k with k = d_j (mod R_j) after.
+  bool pfa = false;
+  std::vector<int> n_of_pos, pos_of_n;   // identity unless pfa
 };
+
+inline bool coprime_schedule(const std::vector<int>& r) {
+  if (r.size() < 2) return false;
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  for (size_t i = 0; i < r.size(); ++i)
+    for (size_t j = i + 1; j < r.size(); ++j)
+      if (gcd(r[i], r[j]) != 1) return false;
+  return true;
+}
+
+// Switch a sub-plan to the prime-factor index maps (the radix schedule and strides stay).
+inline void set_pfa(HostSubPlan& sp) {
+  const int F = sp.F;
+  sp.pfa = true;
+  for (int p = 0; p < F; ++p) {
+    long long n = 0, k = 0;
+    for (size_t j = 0; j < sp.radix.size(); ++j) {
+      const int R = sp.radix[j], d = (p / sp.m[j]) % R, Nj = F / R;
+      n += (long long)d * Nj;
+      k += (long long)d * Nj * modinv(Nj, R);          // CRT: k = d_j (mod R_j)
+    }
+    sp.n_of_pos[p] = (int)(n % F);
+    sp.pos_of_n[(int)(n % F)] = p;
+    sp.freq_of_pos[p] = (int)(k % F);
+    sp.pos_of_freq[(int)(k % F)] = p;
+  }
+}
 
 struct HostPlan {
   int N = 0, N1 = 0, N2 = 0;
@@ -30,7 +63,9 @@ struct HostPlan {
   std::vector<float2> cube_tw0, cube_tw1;
   HostSubPlan s1, s2;                // s1: length N1 over stride-N2 columns; s2: length N2 over rows
   std::vector<float2> tw1, tw2;      // exp(-2 pi i k / F)
-  std::vector<float2> twm;           // twm[p1*N2 + n2] = exp(-2 pi i k1(p1) n2 / N)
+  std::vector<float2> twm;           // twm[p1*N2 + n2] = exp(-2 pi i k1(p1) n2 / N)       (forward: columns are natural n2)
+  std::vector<float2> twm_inv;       // twm_inv[p1*N2 + p2] = exp(-2 pi i k1(p1) n2(p2) / N) (inverse: columns are positions);
+                                     // empty when s2 is not a prime-factor transform (then equal to twm)
 };
 
 inline std::vector<int> prime_factors(int n) {
@@ -74,7 +109,9 @@ inline bool make_subplan(int F, HostSubPlan& sp, unsigned long long disabled = 0
   if (F > 1) search(F, 0);
   bool use_forced = false;
   // schedules measured faster than the rule above (tools/ab_sched.py, bench_configs.py)
-  static const std::vector<std::vector<int>> kMeasured = {{10, 20}, {10, 25}, {11, 20}};
+  // 372 = 31 * 12: with the twiddle-free prime-factor form the in-register radix 12 = 4 x 3 saves a
+  // shared-memory pass over 31 * 3 * 4 (columns kernel 24.7 -> 22.6 us per 32 units of 163680)
+  static const std::vector<std::vector<int>> kMeasured = {{10, 20}, {10, 25}, {11, 20}, {31, 12}};
   if (!disabled)
     for (const auto& m : kMeasured) {
       long long prod = 1;
@@ -110,6 +147,9 @@ inline bool make_subplan(int F, HostSubPlan& sp, unsigned long long disabled = 0
   // frequency k = q0 + r0*(q1 + r1*(q2 + ...)) lands at position sum_j q_j * m_j
   sp.pos_of_freq.assign(F, 0);
   sp.freq_of_pos.assign(F, 0);
+  sp.n_of_pos.resize(F);
+  sp.pos_of_n.resize(F);
+  for (int k = 0; k < F; ++k) { sp.n_of_pos[k] = k; sp.pos_of_n[k] = k; }
   for (int k = 0; k < F; ++k) {
     int rem = k, pos = 0;
     for (size_t j = 0; j < sp.radix.size(); ++j) { pos += (rem % sp.radix[j]) * sp.m[j]; rem /= sp.radix[j]; }
@@ -151,8 +191,11 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
 }
 
 // Choose N = N1*N2 with both factors tile-sized and as square as possible.
+// use_pfa(sub-plan, which): whether the kernels that will run sub-transform `which` (1: length N1,
+// 2: length N2) are the twiddle-free prime-factor ones (asked only for coprime schedules).
 inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, unsigned long long disabled = 0,
-                      const std::vector<int>* sched1 = nullptr, const std::vector<int>* sched2 = nullptr) {
+                      const std::vector<int>* sched1 = nullptr, const std::vector<int>* sched2 = nullptr,
+                      const std::function<bool(const HostSubPlan&, int)>* use_pfa = nullptr) {
   pl = HostPlan();
   pl.N = N;
   if (N < 4) { err = "FFT length must be >= 4"; return false; }
@@ -192,6 +235,10 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
     }
   }
   if (!make_subplan(pl.N1, pl.s1, disabled, sched1) || !make_subplan(pl.N2, pl.s2, disabled, sched2)) { err = "unsupported factorisation"; return false; }
+  if (use_pfa && pl.large) {
+    if (coprime_schedule(pl.s1.radix) && (*use_pfa)(pl.s1, 1)) set_pfa(pl.s1);
+    if (coprime_schedule(pl.s2.radix) && (*use_pfa)(pl.s2, 2)) set_pfa(pl.s2);
+  }
   for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   pl.tw1 = unit_roots(pl.s1);
@@ -204,6 +251,12 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
       double a = -2.0 * M_PI * (double)e / (double)N;
       pl.twm[(size_t)p1 * pl.N2 + n2] = make_float2((float)cos(a), (float)sin(a));
     }
+  }
+  if (pl.s2.pfa) {
+    pl.twm_inv.resize((size_t)N);
+    for (int p1 = 0; p1 < pl.N1; ++p1)
+      for (int p2 = 0; p2 < pl.N2; ++p2)
+        pl.twm_inv[(size_t)p1 * pl.N2 + p2] = pl.twm[(size_t)p1 * pl.N2 + pl.s2.n_of_pos[p2]];
   }
   return true;
 }

@@ -8,6 +8,7 @@
 #include "bank.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -69,7 +70,7 @@ struct gnssacq {
 
   HostPlan hp;
   DevPlan dp{};
-  DevBuf d_tw1, d_tw2, d_twm, d_cube0, d_cube1;
+  DevBuf d_tw1, d_tw2, d_twm, d_twm_inv, d_maps, d_cube0, d_cube1;
   CubeTw cube_tw{nullptr, nullptr};
   DevBuf d_C;                         // replica spectra [R][N]
   int R = 0, N = 0;
@@ -128,13 +129,31 @@ void fill_subplan(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
   }
   sp.tws0_t_off = hs.tws0_t_off;
   sp.tw = tw;
+  sp.pfa = hs.pfa ? 1 : 0;
 }
 
 int upload_plan(gnssacq* h, int N) {
   if (h->hp.N == N && !h->plan_dirty) return 0;
   HostPlan hp;
   std::string err;
-  if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1])) return fail(GNSSACQ_EINVAL, err);
+  // A coprime radix schedule runs as a twiddle-free prime-factor transform when every kernel that
+  // touches that sub-transform is a plan-specialised one (they carry the index maps; the generic
+  // runtime-planned kernels are Cooley-Tukey only).
+  const bool spec = h->use_spec;
+  const std::function<bool(const HostSubPlan&, int)> use_pfa = [spec](const HostSubPlan& hs, int which) {
+    if (!spec) return false;
+    SubPlan sp{};                         // schedule only: the twiddle tables do not exist yet
+    sp.F = hs.F;
+    sp.ns = (int)hs.radix.size();
+    for (int j = 0; j < kMaxStages; ++j) {
+      sp.radix[j] = j < sp.ns ? hs.radix[j] : 1;
+      sp.m[j] = j < sp.ns ? hs.m[j] : 1;
+    }
+    sp.pfa = 1;
+    return which == 1 ? (find_cols_kernel(sp, false) && find_cols_kernel(sp, true) && find_fwd_cols_kernel(sp, 0) && find_fwd_cols_kernel(sp, 1))
+                      : (find_rows_kernel(sp) && find_fwd_rows_kernel(sp));
+  };
+  if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1], &use_pfa)) return fail(GNSSACQ_EINVAL, err);
   h->plan_dirty = false;
   if (int rc = h->d_tw1.ensure(hp.tw1.size() * sizeof(float2))) return rc;
   if (int rc = h->d_tw2.ensure(hp.tw2.size() * sizeof(float2))) return rc;
@@ -142,6 +161,17 @@ int upload_plan(gnssacq* h, int N) {
   CU(cudaMemcpyAsync(h->d_tw1.p, hp.tw1.data(), hp.tw1.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_tw2.p, hp.tw2.data(), hp.tw2.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_twm.p, hp.twm.data(), hp.twm.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  if (!hp.twm_inv.empty()) {
+    if (int rc = h->d_twm_inv.ensure(hp.twm_inv.size() * sizeof(float2))) return rc;
+    CU(cudaMemcpyAsync(h->d_twm_inv.p, hp.twm_inv.data(), hp.twm_inv.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  }
+  // index maps: n1_of_pos [N1], n2_of_pos [N2], pos2_of_n [N2]
+  std::vector<int> maps;
+  maps.insert(maps.end(), hp.s1.n_of_pos.begin(), hp.s1.n_of_pos.end());
+  maps.insert(maps.end(), hp.s2.n_of_pos.begin(), hp.s2.n_of_pos.end());
+  maps.insert(maps.end(), hp.s2.pos_of_n.begin(), hp.s2.pos_of_n.end());
+  if (int rc = h->d_maps.ensure(maps.size() * sizeof(int))) return rc;
+  CU(cudaMemcpyAsync(h->d_maps.p, maps.data(), maps.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (hp.cube) {
     if (int rc = h->d_cube0.ensure(hp.cube_tw0.size() * sizeof(float2))) return rc;
     if (int rc = h->d_cube1.ensure(hp.cube_tw1.size() * sizeof(float2))) return rc;
@@ -155,6 +185,10 @@ int upload_plan(gnssacq* h, int N) {
   fill_subplan(hp.s1, h->d_tw1.as<float2>(), h->dp.s1);
   fill_subplan(hp.s2, h->d_tw2.as<float2>(), h->dp.s2);
   h->dp.twm = h->d_twm.as<float2>();
+  h->dp.twm_inv = hp.twm_inv.empty() ? h->d_twm.as<float2>() : h->d_twm_inv.as<float2>();
+  h->dp.n1_of_pos = h->d_maps.as<int>();
+  h->dp.n2_of_pos = h->d_maps.as<int>() + hp.N1;
+  h->dp.pos2_of_n = h->d_maps.as<int>() + hp.N1 + hp.N2;
   h->hp = std::move(hp);
   return 0;
 }
@@ -431,7 +465,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
+  for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
                     &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank})
     b->release();
@@ -584,7 +618,11 @@ int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, doubl
 
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
-  if (std::string(name) == "specialized_kernels") { h->use_spec = value != 0; return 0; }
+  if (std::string(name) == "specialized_kernels") {     // changes the spectrum layout: replicas must be set again
+    if (h->use_spec != (value != 0)) { h->R = 0; h->plan_dirty = true; }
+    h->use_spec = value != 0;
+    return 0;
+  }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
   if (std::string(name) == "small_ctas") { h->small_ctas = value; return 0; }
   if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
@@ -747,7 +785,7 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
   if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
-  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0);
+  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

@@ -20,7 +20,11 @@ constexpr int kNcoSize = 1024;
 struct DevPlan {
   int N, N1, N2;
   SubPlan s1, s2;
-  const float2* twm;     // twm[p1*N2 + n2]
+  const float2* twm;     // twm[p1*N2 + n2]: forward four-step twiddle (columns = natural n2)
+  const float2* twm_inv; // [p1*N2 + p2]: the same for the inverse, whose columns are tile positions (== twm unless s2.pfa)
+  const int* n1_of_pos;  // time index n1 held at position p1 of the length-N1 tile (identity unless s1.pfa)
+  const int* n2_of_pos;  // likewise for the length-N2 tile
+  const int* pos2_of_n;  // inverse of n2_of_pos
 };
 
 // Per-(replica, doppler, tile) partial result of the correlate kernel.

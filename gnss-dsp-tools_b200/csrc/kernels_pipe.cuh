@@ -230,28 +230,7 @@ k_corr_rows_p(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
     __syncthreads();                       // Xs / Cs consumed, tile complete
     if (it + 1 < it_end) { fence_async_smem(); issue(it + 1); }
     inv_stages_rows8<S, NS - 2, PP, THREADS>(tile, nrows, pl.s2);
-    // ---- last inverse stage fused with the conjugate four-step twiddle and the store
-    {
-      float2* out = scratch + ((long long)ul * B + b) * N + (long long)row0 * N2;
-      const float2* twm = pl.twm + (long long)row0 * N2;
-      constexpr int R0 = S::radix(0), m0 = S::stride(0);
-      static_assert(!is_split_radix(R0), "warp-pair radices belong to the columns transform");
-      const float2* twt = pl.s2.tw + pl.s2.tws0_t_off;
-      const int items = m0 * nrows;
-      for (int id = threadIdx.x; id < items; id += THREADS) {
-        const int c = id / m0, i = id - c * m0;
-        const float2* p = tile + c * PP + i;
-        float2 v[R0];
-#pragma unroll
-        for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
-#pragma unroll
-        for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
-        inv_dft<R0>(v);
-        const int g = c * N2 + i;
-#pragma unroll
-        for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
-      }
-    }
+    rows8_last_stage<S, PP, THREADS>(tile, nrows, pl, scratch + ((long long)ul * B + b) * N + (long long)row0 * N2, row0);
     __syncthreads();                       // tile is rewritten by the next item's first stage
   }
 }

@@ -26,7 +26,7 @@ __device__ __forceinline__ void inv_stage_rows8(float2* tile, int nrows, const f
   const int c = threadIdx.x & 7, tb = threadIdx.x >> 3;
   constexpr int nb = THREADS / 8;
   const float2* tws = twbase + twoff;
-  constexpr bool kHoist = m > 1 && nb % m == 0 && R <= 8;
+  constexpr bool kHoist = !S::kPfa && m > 1 && nb % m == 0 && R <= 8;
   float2 wh[kHoist ? R : 1];
   if constexpr (kHoist) {
     const float2* w = tws + (tb % m) * (R - 1);
@@ -44,7 +44,7 @@ __device__ __forceinline__ void inv_stage_rows8(float2* tile, int nrows, const f
       if constexpr (kHoist) {
 #pragma unroll
         for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], wh[q]);
-      } else if constexpr (m > 1) {
+      } else if constexpr (m > 1 && !S::kPfa) {
         const float2* w = tws + i * (R - 1);
 #pragma unroll
         for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
@@ -61,6 +61,33 @@ __device__ __forceinline__ void inv_stages_rows8(float2* tile, int nrows, const 
   if constexpr (J >= 1) {
     inv_stage_rows8<S, J, PP, THREADS>(tile, nrows, sp.tw, sp.tws_off[J]);
     inv_stages_rows8<S, J - 1, PP, THREADS>(tile, nrows, sp);
+  }
+}
+
+// Last inverse stage of the rows transform (stage 0, stride m0 >= 16) fused with the conjugate
+// four-step twiddle and the store: lanes walk i (consecutive positions), so tile reads, twiddle
+// reads and global stores are contiguous. Prime-factor schedules have no stage twiddle here.
+template <class S, int PP, int THREADS>
+__device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, const DevPlan& pl, float2* __restrict__ out, int row0) {
+  constexpr int N2 = S::F, R0 = S::radix(0), m0 = S::stride(0);
+  static_assert(!is_split_radix(R0), "warp-pair radices belong to the columns transform");
+  const float2* twm = pl.twm_inv + (long long)row0 * N2;
+  const float2* twt = pl.s2.tw + pl.s2.tws0_t_off;
+  const int items = m0 * nrows;
+  for (int id = threadIdx.x; id < items; id += THREADS) {
+    const int c = id / m0, i = id - c * m0;
+    const float2* p = tile + c * PP + i;
+    float2 v[R0];
+#pragma unroll
+    for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
+    if constexpr (!S::kPfa) {
+#pragma unroll
+      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
+    }
+    inv_dft<R0>(v);
+    const int g = c * N2 + i;
+#pragma unroll
+    for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
   }
 }
 
@@ -130,27 +157,7 @@ k_corr_rows_t(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
   }
   __syncthreads();
   inv_stages_rows8<S, NS - 2, PP, THREADS>(tile, nrows, pl.s2);
-  // ---- last inverse stage fused with the conjugate four-step twiddle and the store
-  {
-    float2* out = scratch + ((long long)ul * B + b) * N + (long long)row0 * N2;
-    const float2* twm = pl.twm + (long long)row0 * N2;
-    constexpr int R0 = S::radix(0), m0 = S::stride(0);
-    const float2* twt = pl.s2.tw + pl.s2.tws0_t_off;
-    const int items = m0 * nrows;
-    for (int id = threadIdx.x; id < items; id += THREADS) {
-      const int c = id / m0, i = id - c * m0;
-      const float2* p = tile + c * PP + i;
-      float2 v[R0];
-#pragma unroll
-      for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
-#pragma unroll
-      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
-      inv_dft<R0>(v);
-      const int g = c * N2 + i;
-#pragma unroll
-      for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
-    }
-  }
+  rows8_last_stage<S, PP, THREADS>(tile, nrows, pl, scratch + ((long long)ul * B + b) * N + (long long)row0 * N2, row0);
 }
 
 

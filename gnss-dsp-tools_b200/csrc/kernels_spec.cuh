@@ -27,6 +27,21 @@ struct Sub {
     for (int k = j + 1; k < 4; ++k) m *= radix(k);
     return m;
   }
+  __host__ __device__ static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+  __host__ __device__ static constexpr bool coprime_() {
+    for (int j = 0; j < NS; ++j)
+      for (int k = j + 1; k < NS; ++k)
+        if (gcd_(radix(j), radix(k)) != 1) return false;
+    return true;
+  }
+  // Pairwise-coprime radices: the kernels run the transform in its prime-factor form — a plain
+  // multi-dimensional DFT over the digits of the tile position, no stage twiddles; the host plan
+  // (fft_plan.h::set_pfa) supplies the index maps that go with it.
+#ifdef GNSSACQ_NO_PFA
+  static constexpr bool kPfa = false;       // A/B builds of tools/microbench only
+#else
+  static constexpr bool kPfa = coprime_();
+#endif
 };
 
 constexpr bool is_split_radix(int R) { return R == 31; }
@@ -50,14 +65,14 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
   constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
   const int tc = threadIdx.x & (kTW - 1);
   if constexpr (is_split_radix(R)) {
-    stage_tile_split<R, true, ES, CS>(tile, ncols, S::F, m, twbase);   // warp-pair version, W_F table
+    stage_tile_split<R, true, ES, CS, S::kPfa>(tile, ncols, S::F, m, twbase);   // warp-pair version, W_F table
   } else {
     const int tb = threadIdx.x / kTW;
     constexpr int nb = THREADS / kTW;
     const float2* tws = twbase + twoff;
     // When the butterfly stride divides the 16 butterfly groups, a thread meets the same
     // twiddle row in every iteration (i = tb mod m): load it once.
-    constexpr bool kHoist = m > 1 && nb % m == 0 && R <= 8;
+    constexpr bool kHoist = !S::kPfa && m > 1 && nb % m == 0 && R <= 8;
     float2 wh[kHoist ? R : 1];
     if constexpr (kHoist) {
       const float2* w = tws + (tb % m) * (R - 1);
@@ -75,7 +90,7 @@ __device__ __forceinline__ void inv_stage_smem(float2* tile, int ncols, const fl
         if constexpr (kHoist) {
 #pragma unroll
           for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], wh[q]);
-        } else if constexpr (m > 1) {
+        } else if constexpr (m > 1 && !S::kPfa) {
           const float2* w = tws + i * (R - 1);
 #pragma unroll
           for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
@@ -135,7 +150,7 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
   inv_stages_smem<S, NS - 1, 1, 1, P>(tile, nrows, pl.s2);
   // ---- last inverse stage (first forward stage, stride m0)
   float2* out = scratch + ((long long)ul * B + b) * N + (long long)row0 * N2;
-  const float2* twm = pl.twm + (long long)row0 * N2;
+  const float2* twm = pl.twm_inv + (long long)row0 * N2;
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
   if constexpr (!is_split_radix(R0) && m0 >= 16) {
     // fused with the conjugate four-step twiddle and the store: lanes walk i (consecutive n2),
@@ -148,8 +163,10 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
       float2 v[R0];
 #pragma unroll
       for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
+      if constexpr (!S::kPfa) {
 #pragma unroll
-      for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
+        for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
+      }
       inv_dft<R0>(v);
       const int g = c * N2 + i;
 #pragma unroll
@@ -194,18 +211,36 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
   constexpr int nb = THREADS / kTW;
   const bool dump = qd != nullptr;
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
-  auto sink = [&](int n1, float2 v) {
+  // A butterfly output sits at tile position pos = i + q*m0; the lag it stands for is
+  // n1 * N2 + n2 with the time indices of that position and of this thread's column. Prime-factor
+  // plans: n1 = (n1_of_pos[i] + q * F/R0) mod F (one table read per butterfly, outside the
+  // peak-search branch: with ~46 outputs per thread and tile, some lane of a warp takes that
+  // branch for most outputs, so its body must stay a few integer instructions);
+  // Cooley-Tukey plans: n1 = pos, n2 = column.
+  const int lagc = (S::kPfa && tc < ncols) ? __ldg(&pl.n2_of_pos[lag0]) : lag0;
+  auto n1_base = [&](int i) -> int { if constexpr (S::kPfa) return __ldg(&pl.n1_of_pos[i]); else return i; };
+  auto n1_of = [&](int n1i, int q) -> int {
+    if constexpr (S::kPfa) { const int n = n1i + q * (S::F / R0); return n >= S::F ? n - S::F : n; }
+    else return n1i + q * m0;
+  };
+  auto sink = [&](int pos, int n1, float2 v) {
     float acc = sqrt_fast(v.x * v.x + v.y * v.y);
     if (MULTI) {
-      if (b > 0) acc += qs[n1 * WP + tc];
-      if (!last) { qs[n1 * WP + tc] = acc; return; }
+      if (b > 0) acc += qs[pos * WP + tc];
+      if (!last) { qs[pos * WP + tc] = acc; return; }
     }
     sum += acc;
-    if (acc >= best) {                       // rare after the first few samples
-      const int lag = n1 * N2 + lag0;
+    if (acc >= best) {                       // per thread rare after its first few outputs
+      const int lag = n1 * N2 + lagc;
       if (lag < n_lags && (acc > best || lag < bestlag)) { best = acc; bestlag = lag; }
     }
-    if (dump) qd[n1 * N2 + lag0] = acc * scale;
+    if (dump) qd[n1 * N2 + lagc] = acc * scale;
+  };
+  // leg q of the butterfly at tile offset p, conjugate stage twiddle applied unless prime-factor
+  auto leg = [&](const float2* p, const float2* w, int q) -> float2 {
+    float2 v = p[q * m0 * WP];
+    if constexpr (!S::kPfa) v = cmulc(v, __ldg(&w[q - 1]));
+    return v;
   };
   if constexpr (is_split_radix(R0) && SPLIT) {
     // warp-pair butterfly (see stage_tile_split): both warps load, each emits half the outputs
@@ -222,12 +257,13 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
         const float2 x0 = cswap(p[0]);
         static_for<1, H + 1>([&](auto J) {
           constexpr int j = decltype(J)::value;
-          const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
-          const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
+          const float2 s = cswap(leg(p, w, j));
+          const float2 t = cswap(leg(p, w, R0 - j));
           a[j] = cadd(s, t);
           bq[j] = csub(s, t);
         });
-        auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };      // |.| ignores the re/im swap
+        const int n1i = n1_base(i);
+        auto emit = [&](int q, float2 v) { sink(i + q * m0, n1_of(n1i, q), v); };      // |.| ignores the re/im swap
         if (role == 0) {
           float2 s0 = x0;
           static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
@@ -251,13 +287,14 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
         float2 s0 = x0;
         static_for<1, H + 1>([&](auto J) {
           constexpr int j = decltype(J)::value;
-          const float2 s = cswap(cmulc(p[j * m0 * WP], __ldg(&w[j - 1])));
-          const float2 t = cswap(cmulc(p[(R0 - j) * m0 * WP], __ldg(&w[R0 - j - 1])));
+          const float2 s = cswap(leg(p, w, j));
+          const float2 t = cswap(leg(p, w, R0 - j));
           a[j] = cadd(s, t);
           bq[j] = csub(s, t);
           s0 = cadd(s0, a[j]);
         });
-        auto emit = [&](int q, float2 v) { sink(i + q * m0, v); };
+        const int n1i = n1_base(i);
+        auto emit = [&](int q, float2 v) { sink(i + q * m0, n1_of(n1i, q), v); };
         emit(0, s0);
         prime_outputs<R0, 1, H>(x0, a, bq, emit);
       }
@@ -271,14 +308,17 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
         float2 v[R0];
 #pragma unroll
         for (int q = 0; q < R0; ++q) v[q] = p[q * m0 * WP];
-        const float2* w = tws + i * (R0 - 1);
+        if constexpr (!S::kPfa) {
+          const float2* w = tws + i * (R0 - 1);
 #pragma unroll
-        for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+          for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&w[q - 1]));
+        }
 #pragma unroll
         for (int q = 0; q < R0; ++q) v[q] = cswap(v[q]);
         Dft<R0>::run(v);                                                 // |.| ignores the swap back
+        const int n1i = n1_base(i);
 #pragma unroll
-        for (int q = 0; q < R0; ++q) sink(i + q * m0, v[q]);
+        for (int q = 0; q < R0; ++q) sink(i + q * m0, n1_of(n1i, q), v[q]);
       }
     }
   }
@@ -351,7 +391,7 @@ __device__ __forceinline__ void fwd_stage_smem(float2* tile, int ncols, const fl
   constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
   const int tc = threadIdx.x & (kTW - 1);
   if constexpr (is_split_radix(R)) {
-    stage_tile_split<R, false, ES, CS>(tile, ncols, S::F, m, twbase);
+    stage_tile_split<R, false, ES, CS, S::kPfa>(tile, ncols, S::F, m, twbase);
   } else {
     const int tb = threadIdx.x / kTW;
     constexpr int nb = kThreads / kTW;
@@ -365,7 +405,7 @@ __device__ __forceinline__ void fwd_stage_smem(float2* tile, int ncols, const fl
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = p[q * m * ES];
         Dft<R>::run(v);
-        if constexpr (m > 1) {
+        if constexpr (m > 1 && !S::kPfa) {
           const float2* w = tws + i * (R - 1);
 #pragma unroll
           for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(&w[q - 1]));
@@ -405,10 +445,12 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
   if (SRC == 0) { const int d = t / B, b = t - d * B; base = (long long)b * stride; f = freq[d]; }
   else { base = (long long)t * N; }
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
+  // tile position p1 takes time sample n1_of_pos[p1] (identity unless the plan is prime-factor)
+  auto n1_at = [&](int p1) -> int { if constexpr (S::kPfa) return __ldg(&pl.n1_of_pos[p1]); else return p1; };
   if constexpr (is_split_radix(R0)) {
     if (tc < ncols)
       for (int n1 = tb; n1 < N1; n1 += nb)
-        tile[n1 * WP + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n1 * N2 + col0 + tc);
+        tile[n1 * WP + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n1_at(n1) * N2 + col0 + tc);
     __syncthreads();
     fwd_stage_smem<S, 0, WP, 1>(tile, ncols, pl.s1.tw, pl.s1.tws_off[0]);
   } else {
@@ -419,11 +461,13 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
       for (int i = tb; i < m0; i += nb) {
         float2 v[R0];
 #pragma unroll
-        for (int q = 0; q < R0; ++q) v[q] = load_input<SRC>(x, rep, nco_tab, f, base, (i + q * m0) * N2 + col0 + tc);
+        for (int q = 0; q < R0; ++q) v[q] = load_input<SRC>(x, rep, nco_tab, f, base, n1_at(i + q * m0) * N2 + col0 + tc);
         Dft<R0>::run(v);
-        const float2* w = tws + i * (R0 - 1);
+        if constexpr (!S::kPfa) {
+          const float2* w = tws + i * (R0 - 1);
 #pragma unroll
-        for (int q = 1; q < R0; ++q) v[q] = cmul(v[q], __ldg(&w[q - 1]));
+          for (int q = 1; q < R0; ++q) v[q] = cmul(v[q], __ldg(&w[q - 1]));
+        }
 #pragma unroll
         for (int q = 0; q < R0; ++q) tile[(i + q * m0) * WP + tc] = v[q];
       }
@@ -462,9 +506,14 @@ k_fwd_rows_s(DevPlan pl, float2* __restrict__ X) {
   const int row0 = blockIdx.x * kTileW;
   const int nrows = imin(kTileW, N1 - row0);
   float2* Xt = X + (long long)blockIdx.y * N + (long long)row0 * N2;
+  // time sample n2 goes to tile position pos2_of_n[n2] (identity unless the plan is prime-factor)
   for (int c = tb; c < nrows; c += nb) {
 #pragma unroll 8
-    for (int e = tc; e < N2; e += kTW) tile[c * P + e] = Xt[c * N2 + e];
+    for (int e = tc; e < N2; e += kTW) {
+      int pe = e;
+      if constexpr (S::kPfa) pe = __ldg(&pl.pos2_of_n[e]);
+      tile[c * P + pe] = Xt[c * N2 + e];
+    }
   }
   __syncthreads();
   fwd_stages_smem<S, 0, NS - 1, 1, P>(tile, nrows, pl.s2);
@@ -486,6 +535,7 @@ using S186 = Sub<186, 31, 6>;
 using S220 = Sub<220, 11, 20>;
 using S279 = Sub<279, 31, 9>;
 using S372 = Sub<372, 31, 3, 4>;
+using S372b = Sub<372, 31, 12>;          // radix 12 = 4 x 3 in registers: one shared-memory pass fewer
 using S440 = Sub<440, 11, 5, 8>;
 using S200 = Sub<200, 10, 20>;
 using S250 = Sub<250, 10, 25>;
@@ -493,7 +543,7 @@ using S248 = Sub<248, 31, 8>;
 using S496 = Sub<496, 31, 16>;
 
 template <class S> inline bool schedule_matches(const SubPlan& sp) {
-  if (sp.F != S::F || sp.ns != S::NS) return false;
+  if (sp.F != S::F || sp.ns != S::NS || (sp.pfa != 0) != S::kPfa) return false;
   for (int j = 0; j < S::NS; ++j)
     if (sp.radix[j] != S::radix(j) || sp.m[j] != S::stride(j)) return false;
   return true;

@@ -7,7 +7,7 @@
 namespace acq {
 
 #define COLS_LIST_0(T) T(S128) T(S256) T(S320) T(S165)
-#define COLS_LIST_1(T) T(S220) T(S372) T(S200) T(S248)
+#define COLS_LIST_1(T) T(S220) T(S372b) T(S200) T(S248)
 #define COLS_LIST_2(T) T(S496) T(S186) T(S279)
 
 corr_cols_fn find_cols_part0(const SubPlan&, bool);
@@ -21,7 +21,7 @@ constexpr int kColsSmallThreads = 128;
 #if GNSSACQ_REG_PART == 0
 fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
 #define TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
-  TRY(S128) TRY(S256) TRY(S320) TRY(S165) TRY(S220) TRY(S372) TRY(S200) TRY(S248) TRY(S496) TRY(S186) TRY(S279)
+  TRY(S128) TRY(S256) TRY(S320) TRY(S165) TRY(S220) TRY(S372b) TRY(S200) TRY(S248) TRY(S496) TRY(S186) TRY(S279)
 #undef TRY
   return nullptr;
 }
@@ -81,7 +81,7 @@ corr_cols_fn find_cols_small_part0(const SubPlan& s1, bool multi) {
   return nullptr;
 }
 #elif GNSSACQ_REG_PART == 6
-corr_cols_fn find_cols_small_part1(const SubPlan& s1, bool multi) { TRY(S372) TRY(S200) TRY(S248) return nullptr; }
+corr_cols_fn find_cols_small_part1(const SubPlan& s1, bool multi) { TRY(S372b) TRY(S200) TRY(S248) return nullptr; }
 #else
 corr_cols_fn find_cols_small_part2(const SubPlan& s1, bool multi) { COLS_LIST_2(TRY) return nullptr; }
 #endif

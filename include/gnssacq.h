@@ -142,7 +142,8 @@ int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
 /* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =
  * specialised columns kernel; 4 = the 16x16x16 single-CTA kernels (N = 4096); 0 = generic
- * runtime-planned kernels. Negative on error. */
+ * runtime-planned kernels; bit 3 / bit 4 = the length-N1 / length-N2 tile transform runs in its
+ * twiddle-free prime-factor form (coprime radix schedule). Negative on error. */
 int gnssacq_kernel_variant(gnssacq_t* h);
 int gnssacq_synchronize(gnssacq_t* h);
 /* Tuning switches, for tests and A/B measurements. "specialized_kernels" (default 1): use the

@@ -81,6 +81,11 @@ static inline unsigned long long atomicMax(unsigned long long* a, unsigned long 
   while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }
+static inline unsigned atomicMax(unsigned* a, unsigned v) {
+  unsigned old = __atomic_load_n(a, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 static inline float atomicAdd(float* a, float v) {
   static std::mutex mu; std::lock_guard<std::mutex> g(mu);
   float old = *a; *a = old + v; return old;

@@ -69,6 +69,15 @@ def test_large_pow2_padded(eng):
 def test_large_61380_like_l5(eng):
     info = _case(eng, 30690, True, False, False, 2, (-400, 400, 400), 30.69e6, nprn=1)
     assert info['large'] and info['N'] == 61380
+    # 279 = 31*9 and 220 = 11*20 are coprime schedules: both tile transforms run twiddle-free (prime-factor)
+    assert eng.kernel_variant() & 24 == 24
+    # the generic Cooley-Tukey kernels must agree with the prime-factor ones
+    eng.set_option('specialized_kernels', 0)
+    try:
+        _case(eng, 30690, True, False, False, 2, (-400, 400, 400), 30.69e6, nprn=1)
+        assert eng.kernel_variant() == 0
+    finally:
+        eng.set_option('specialized_kernels', 1)
 
 
 def test_large_lag_limit(eng):
@@ -163,3 +172,11 @@ def test_serial_searches_match_oracle(eng):
     got = acquire_serial.search_glonass_p(x, chan, doppler, ca, ms, fs, 562500, engine=eng, hypotheses=10)
     want = orc.search_glonass_p(x, gp.p_code(), fs, 562500, chan, doppler, ca, ms, hypotheses=10)
     assert got[1] == want[1] == 6 and abs(got[0] - want[0]) <= 1e-4 * want[0]
+
+
+@pytest.mark.slow
+def test_large_163680_prime_factor_31x12(eng):
+    """BASELINE config 2's transform: 163680 = 372 x 440 with 372 = 31*12 and 440 = 11*5*8, both
+    twiddle-free prime-factor schedules (small-CTA kernels, radix 12 in registers)."""
+    info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
+    assert info['N1'] == 372 and info['N2'] == 440 and eng.kernel_variant() == 27

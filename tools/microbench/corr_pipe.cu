@@ -35,7 +35,7 @@ static void fill_sub(const HostSubPlan& hs, const float2* tw, SubPlan& sp) {
   for (int j = 0; j < kMaxStages; ++j) {
     sp.radix[j] = j < sp.ns ? hs.radix[j] : 1; sp.m[j] = j < sp.ns ? hs.m[j] : 1; sp.tws_off[j] = j < sp.ns ? hs.tws_off[j] : 0;
   }
-  sp.tws0_t_off = hs.tws0_t_off; sp.tw = tw;
+  sp.tws0_t_off = hs.tws0_t_off; sp.tw = tw; sp.pfa = hs.pfa ? 1 : 0;
 }
 template <class T> T* dev(const std::vector<T>& v) {
   T* p; CK(cudaMalloc(&p, v.size() * sizeof(T))); CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return p;
@@ -46,10 +46,24 @@ int main(int argc, char** argv) {
   const int U = argc > 1 ? atoi(argv[1]) : 32;      // units per launch
   const int reps = argc > 2 ? atoi(argv[2]) : 40;
   HostPlan hp; std::string err;
-  if (!make_plan(N, hp, err)) { printf("plan: %s\n", err.c_str()); return 1; }
+  #ifdef GNSSACQ_NO_PFA
+  const std::function<bool(const HostSubPlan&, int)> use_pfa = [](const HostSubPlan&, int) { return false; };
+#else
+  const std::function<bool(const HostSubPlan&, int)> use_pfa = [](const HostSubPlan&, int) { return true; };
+#endif
+#ifdef SCHED1
+  const std::vector<int> sched1 = {SCHED1, SCHED1B};
+  const std::vector<int>* ps1 = &sched1;
+#else
+  const std::vector<int>* ps1 = nullptr;
+#endif
+  if (!make_plan(N, hp, err, 0, 0, ps1, nullptr, &use_pfa)) { printf("plan: %s\n", err.c_str()); return 1; }
   printf("N=%d plan %dx%d  U=%d B=%d\n", N, hp.N1, hp.N2, U, B);
   DevPlan dp{}; dp.N = N; dp.N1 = hp.N1; dp.N2 = hp.N2;
   fill_sub(hp.s1, dev(hp.tw1), dp.s1); fill_sub(hp.s2, dev(hp.tw2), dp.s2); dp.twm = dev(hp.twm);
+  dp.twm_inv = hp.twm_inv.empty() ? dp.twm : dev(hp.twm_inv);
+  dp.n1_of_pos = dev(hp.s1.n_of_pos); dp.n2_of_pos = dev(hp.s2.n_of_pos); dp.pos2_of_n = dev(hp.s2.pos_of_n);
+  printf("prime-factor: N1 %d, N2 %d\n", (int)hp.s1.pfa, (int)hp.s2.pfa);
   if (!schedule_matches<SCOLS>(dp.s1) || !schedule_matches<SROWS>(dp.s2)) { printf("schedule mismatch\n"); return 1; }
   std::mt19937 rng(1);
   std::normal_distribution<float> nd(0.f, 1.f);
@@ -73,6 +87,8 @@ int main(int argc, char** argv) {
   const size_t smrp = rows_pipe_smem<SROWS>();
   CK(cudaFuncSetAttribute(krowsp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smrp));
   auto krowst = k_corr_rows_t<SROWS, TTHREADS, TMINCTAS>;
+  auto kcolst = k_corr_cols_s<SCOLS, kMulti, 128, 4, false>;
+  CK(cudaFuncSetAttribute(kcolst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)hp.N1 * kTileW * (sizeof(float2) + (kMulti ? sizeof(float) : 0)))));
   const size_t smrt = rows_t_smem<SROWS>();
   CK(cudaFuncSetAttribute(krowst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smrt));
   float2* scr2;
@@ -127,6 +143,8 @@ int main(int argc, char** argv) {
   time("cols (spec)", [&] { run_cols(0); });
   time("cols (pipelined)", [&] { run_colsp(0); });
   time("rows (small CTAs)", [&] { run_rowst(0, scr); });
+  time("cols (small CTAs)", [&] { kcolst<<<dim3(ntiles, U), 128, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
+  time("rows+cols (small CTAs)", [&] { run_rowst(0, scr); kcolst<<<dim3(ntiles, U), 128, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
   time("rows (pipelined)", [&] { run_rowsp(0, scr); });
   time("rows+cols (both pipelined)", [&] { run_rowsp(0, scr); run_colsp(0); });
   time("rows+cols (spec)", [&] { run_rows(0); run_cols(0); });
