@@ -4,7 +4,7 @@
 # Kernels are profiled serialised (overlap_chunks=0) so each launch is one kernel on an idle GPU.
 set -x
 mkdir -p gpurun_out
-TAG=${1:-r01}
+TAG=${1:-r02}
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/bench_under_ncu_${TAG}.log 2>&1

@@ -28,3 +28,12 @@ eng.preprocess(raw, -0.01, 0.0, np.ones(161) / 161, 1.25, 20000)
 xs = (rng.normal(0, 8, 5000) + 1j * rng.normal(0, 8, 5000)).astype(np.complex64)
 eng.mix(xs, 0.123, 0.0)
 print('front end + mix done')
+# replica builder and correlator bank
+eng.set_option('specialized_kernels', 1)
+chips = rng.integers(0, 2, (2, 1023)).astype(np.int8)
+eng.set_signal((rng.normal(0, 8, 3 * 4092) + 1j * rng.normal(0, 8, 3 * 4092)).astype(np.complex64))
+eng.set_replicas_from_chips(chips, 4092, 8184, 1023.0 / 4092, boc=True)
+print('builder', eng.search(-np.arange(2) * 1e-5, 4092, 2, False)[1])
+long_code = rng.integers(0, 2, 767250).astype(np.int8)
+base = rng.uniform(0, 767250, (5, 2))
+print('bank', np.abs(eng.correlate_bank(long_code, -1e-3, 6000, 2, 6000, base, 0.125))[:, 0])
