@@ -396,7 +396,12 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
     // (16 B per cell-block) costs far less than an under-filled grid.
     const size_t budget = h->overlap ? h->scratch_bytes / h->nlanes : h->scratch_bytes;
     const size_t unit_bytes = tbytes * B;
-    const size_t fill = (size_t)(4 * h->num_sms + ntiles - 1) / ntiles;
+    // The 128-thread columns kernel runs 4 CTAs per SM: size a launch to just under one full wave
+    // of them — 95 %, so that the other lane's rows kernel finds free slots at once — not just over
+    // (measured on config 2, profiles/r02_units_per_chunk_sweep.log: 20 units 2.94 ms, 21-64 units 3.03-3.12 ms).
+    const bool small_cols = h->use_spec && (h->small_ctas & 2) && find_cols_small(p.s1, B > 1).fn != nullptr;
+    const size_t fill = small_cols ? std::max<size_t>(1, (size_t)(4 * h->num_sms * 19 / 20) / ntiles)
+                                   : (size_t)(4 * h->num_sms + ntiles - 1) / ntiles;
     size_t uc = std::max(budget / unit_bytes, fill);
     uc = std::min(uc, std::max<size_t>(1, ((size_t)3 << 30) / unit_bytes));      // hard cap 3 GiB per lane
     if (h->force_uc > 0) uc = (size_t)h->force_uc;
