@@ -337,21 +337,47 @@ __device__ __forceinline__ void stage_tile(float2* tile, int WP, int ncols, int 
 // butterfly: both load all P inputs and form the a/b halves, then the even warp produces
 // outputs {0, 1..K0, P-1..P-K0} and the odd warp the rest — no exchange, half the
 // accumulators each. A block barrier separates the loads from the in-place stores.
-template <int P, int K0, int K1, class Emit>
-__device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, const float2* b, Emit&& emit) {
+// Output pairs (k, P-k) for k = K0..K1, produced kPrimeBatch pairs at a time: each pair is two
+// dependent chains of H packed FMAs, so a batch keeps 2 * kPrimeBatch independent chains in flight.
+// batch(k0, nk, re, im) receives integral constants k0, nk and the accumulators of pairs
+// k0 .. k0+nk-1: output k = re - i*im, output P-k = re + i*im.
+#ifdef GNSSACQ_PRIME_BATCH
+constexpr int kPrimeBatch = GNSSACQ_PRIME_BATCH;      // A/B builds of tools/microbench only
+#else
+constexpr int kPrimeBatch = 3;
+#endif
+template <int P, int K0, int K1, class Batch>
+__device__ __forceinline__ void prime_outputs_batched(const float2 x0, const float2* a, const float2* b, Batch&& batch) {
   constexpr int H = (P - 1) / 2;
-  static_for<K0, K1 + 1>([&](auto K) {
-    constexpr int k = decltype(K)::value;
-    float2 re = x0, im = make_float2(0.f, 0.f);
+  constexpr int NK = K1 - K0 + 1;
+  static_for<0, (NK + kPrimeBatch - 1) / kPrimeBatch>([&](auto G) {
+    constexpr int k0 = K0 + decltype(G)::value * kPrimeBatch;
+    constexpr int nk = (K1 - k0 + 1) < kPrimeBatch ? (K1 - k0 + 1) : kPrimeBatch;
+    float2 re[nk], im[nk];
+#pragma unroll
+    for (int t = 0; t < nk; ++t) { re[t] = x0; im[t] = make_float2(0.f, 0.f); }
     static_for<1, H + 1>([&](auto J) {
       constexpr int j = decltype(J)::value;
-      constexpr float c = kTrig<P>.c[(j * k) % P];
-      constexpr float sn = kTrig<P>.s[(j * k) % P];
-      re = cfma_real(c, a[j], re);
-      im = cfma_real(sn, b[j], im);
+      static_for<0, nk>([&](auto T) {
+        constexpr int t = decltype(T)::value, k = k0 + t;
+        constexpr float c = kTrig<P>.c[(j * k) % P];
+        constexpr float sn = kTrig<P>.s[(j * k) % P];
+        re[t] = cfma_real(c, a[j], re[t]);
+        im[t] = cfma_real(sn, b[j], im[t]);
+      });
     });
-    emit(k, make_float2(re.x + im.y, re.y - im.x));
-    emit(P - k, make_float2(re.x - im.y, re.y + im.x));
+    batch(std::integral_constant<int, k0>{}, std::integral_constant<int, nk>{}, re, im);
+  });
+}
+template <int P, int K0, int K1, class Emit>
+__device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, const float2* b, Emit&& emit) {
+  prime_outputs_batched<P, K0, K1>(x0, a, b, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
+    constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
+    static_for<0, nk>([&](auto T) {
+      constexpr int t = decltype(T)::value, k = k0 + t;
+      emit(k, make_float2(re[t].x + im[t].y, re[t].y - im[t].x));
+      emit(P - k, make_float2(re[t].x - im[t].y, re[t].y + im[t].x));
+    });
   });
 }
 

@@ -17,6 +17,11 @@ namespace acq {
 // 8-byte accesses (half-warps). Thread = (row c = tid & 7, butterfly tid >> 3) except in the
 // last stage, where lanes walk the row so that the global stores are contiguous.
 constexpr int kRowsTile8 = 8;
+#ifdef GNSSACQ_ROWS_LOAD_UNROLL
+constexpr int kRowsLoadUnroll = GNSSACQ_ROWS_LOAD_UNROLL;     // A/B builds of tools/microbench only
+#else
+constexpr int kRowsLoadUnroll = 4;                            // 16-byte loads in flight per thread and operand
+#endif
 template <class S> __host__ __device__ constexpr int rows8_pitch() { return S::F + ((2 - S::F % 4) + 4) % 4; }
 
 template <class S, int J, int PP, int THREADS>
@@ -118,7 +123,7 @@ k_corr_rows_t(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
     constexpr int H2 = N2 / 2;
     float4* t4 = reinterpret_cast<float4*>(tile);
     const int n4 = nrows * H2;
-#pragma unroll 4
+#pragma unroll (kRowsLoadUnroll)
     for (int idx = threadIdx.x; idx < n4; idx += THREADS) {
       const int c = idx / H2, e2 = idx - c * H2;
       const float4 cc = __ldg(&Cr[idx]), xx = __ldg(&Xb[idx]);

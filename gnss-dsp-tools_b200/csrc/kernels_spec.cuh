@@ -223,18 +223,64 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
     if constexpr (S::kPfa) { const int n = n1i + q * (S::F / R0); return n >= S::F ? n - S::F : n; }
     else return n1i + q * m0;
   };
-  auto sink = [&](int pos, int n1, float2 v) {
-    float acc = sqrt_fast(v.x * v.x + v.y * v.y);
+  // Peak search over a batch of NB butterfly outputs v[t] (output index q = qof(t), tile position
+  // i + q*m0). Per output the common path is |v|, the sum and one max; one branch per batch asks
+  // whether anything in it reaches the threshold — this thread's best, raised to the best any
+  // converged lane of the warp holds (a hint that never exceeds the tile maximum, so no candidate
+  // for the tile's (max, lowest lag) is skipped). Per-output branches serialise the |.| latency
+  // chains and, with ~46 outputs per thread and tile, some lane of a warp takes them for most
+  // outputs; per batch with the warp-wide threshold the slow path runs for a few batches per tile.
+  auto sink_batch = [&](auto NBc, auto qof, const float2* v, int i, int n1i) {
+    constexpr int NB = decltype(NBc)::value;
+    float acc[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(v[t].x * v[t].x + v[t].y * v[t].y);
     if (MULTI) {
-      if (b > 0) acc += qs[pos * WP + tc];
-      if (!last) { qs[pos * WP + tc] = acc; return; }
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        const int pos = i + qof(t) * m0;
+        if (b > 0) acc[t] += qs[pos * WP + tc];
+        if (!last) qs[pos * WP + tc] = acc[t];
+      }
+      if (!last) return;
     }
-    sum += acc;
-    if (acc >= best) {                       // per thread rare after its first few outputs
-      const int lag = n1 * N2 + lagc;
-      if (lag < n_lags && (acc > best || lag < bestlag)) { best = acc; bestlag = lag; }
+    float m = acc[0];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) { sum += acc[t]; m = fmaxf(m, acc[t]); }
+#if defined(__CUDA_ARCH__)
+    const float thr = fmaxf(best, __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(fmaxf(best, 0.f)))));
+#else
+    const float thr = best;
+#endif
+    if (m >= thr) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        if (acc[t] >= best) {
+          const int lag = n1_of(n1i, qof(t)) * N2 + lagc;
+          if (lag < n_lags && (acc[t] > best || lag < bestlag)) { best = acc[t]; bestlag = lag; }
+        }
+      }
     }
-    if (dump) qd[n1 * N2 + lagc] = acc * scale;
+    if (dump) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) qd[n1_of(n1i, qof(t)) * N2 + lagc] = acc[t] * scale;
+    }
+  };
+  // batch handler for prime_outputs_batched: pairs k0..k0+nk-1 -> outputs k and R0-k (|.| ignores the re/im swap)
+  auto prime_batch = [&](int i, int n1i) {
+    return [&, i, n1i](auto K0c, auto NKc, const float2* re, const float2* im) {
+      constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
+      float2 v[2 * nk];
+#pragma unroll
+      for (int t = 0; t < nk; ++t) {
+        v[2 * t] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);
+        v[2 * t + 1] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);
+      }
+      sink_batch(std::integral_constant<int, 2 * nk>{}, [](int t) { return (t & 1) ? R0 - (k0 + t / 2) : k0 + t / 2; }, v, i, n1i);
+    };
+  };
+  auto sink_one = [&](int q, float2 v, int i, int n1i) {
+    sink_batch(std::integral_constant<int, 1>{}, [q](int) { return q; }, &v, i, n1i);
   };
   // leg q of the butterfly at tile offset p, conjugate stage twiddle applied unless prime-factor
   auto leg = [&](const float2* p, const float2* w, int q) -> float2 {
@@ -263,14 +309,13 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
           bq[j] = csub(s, t);
         });
         const int n1i = n1_base(i);
-        auto emit = [&](int q, float2 v) { sink(i + q * m0, n1_of(n1i, q), v); };      // |.| ignores the re/im swap
         if (role == 0) {
           float2 s0 = x0;
           static_for<1, H + 1>([&](auto J) { s0 = cadd(s0, a[decltype(J)::value]); });
-          emit(0, s0);
-          prime_outputs<R0, 1, KA>(x0, a, bq, emit);
+          sink_one(0, s0, i, n1i);
+          prime_outputs_batched<R0, 1, KA>(x0, a, bq, prime_batch(i, n1i));
         } else {
-          prime_outputs<R0, KA + 1, H>(x0, a, bq, emit);
+          prime_outputs_batched<R0, KA + 1, H>(x0, a, bq, prime_batch(i, n1i));
         }
       }
     }
@@ -294,9 +339,8 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
           s0 = cadd(s0, a[j]);
         });
         const int n1i = n1_base(i);
-        auto emit = [&](int q, float2 v) { sink(i + q * m0, n1_of(n1i, q), v); };
-        emit(0, s0);
-        prime_outputs<R0, 1, H>(x0, a, bq, emit);
+        sink_one(0, s0, i, n1i);
+        prime_outputs_batched<R0, 1, H>(x0, a, bq, prime_batch(i, n1i));
       }
     }
   } else {
@@ -316,9 +360,7 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
 #pragma unroll
         for (int q = 0; q < R0; ++q) v[q] = cswap(v[q]);
         Dft<R0>::run(v);                                                 // |.| ignores the swap back
-        const int n1i = n1_base(i);
-#pragma unroll
-        for (int q = 0; q < R0; ++q) sink(i + q * m0, n1_of(n1i, q), v[q]);
+        sink_batch(std::integral_constant<int, R0>{}, [](int t) { return t; }, v, i, n1_base(i));
       }
     }
   }

@@ -55,7 +55,7 @@ corr_rows_fn find_rows_kernel(const SubPlan& s2) {
 RowsSmall find_rows_small(const SubPlan& s2) {
   static_assert(kRowsSmallTile == kRowsTile8, "row tile");
 #define TRY(S, T, C) if (schedule_matches<S>(s2)) return RowsSmall{k_corr_rows_t<S, T, C>, T, rows_t_smem<S>()};
-  TRY(S440, 160, 5) TRY(S128, 128, 6) TRY(S512, 128, 6) TRY(S320, 128, 6) TRY(S220, 128, 4) TRY(S250, 128, 4)
+  TRY(S440, 192, 5) TRY(S128, 128, 6) TRY(S512, 128, 6) TRY(S320, 128, 6) TRY(S220, 128, 4) TRY(S250, 128, 4)
 #undef TRY
   return RowsSmall{nullptr, 0, 0};
 }
