@@ -82,6 +82,7 @@ __device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, 
   for (int id = threadIdx.x; id < items; id += THREADS) {
     const int c = id / m0, i = id - c * m0;
     const float2* p = tile + c * PP + i;
+    const int g = c * N2 + i;
     float2 v[R0];
 #pragma unroll
     for (int q = 0; q < R0; ++q) v[q] = p[q * m0];
@@ -90,7 +91,6 @@ __device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, 
       for (int q = 1; q < R0; ++q) v[q] = cmulc(v[q], __ldg(&twt[(q - 1) * m0 + i]));
     }
     inv_dft<R0>(v);
-    const int g = c * N2 + i;
 #pragma unroll
     for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
   }

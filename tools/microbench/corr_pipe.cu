@@ -23,6 +23,11 @@ using namespace acq;
 #define TTHREADS 128
 #define TMINCTAS 7
 #endif
+#ifndef CTHREADS
+#define CTHREADS 128
+#define CMINCTAS 4
+#define CSPLIT false
+#endif
 #ifndef BLOCKS
 #define BLOCKS 1
 #endif
@@ -87,7 +92,7 @@ int main(int argc, char** argv) {
   const size_t smrp = rows_pipe_smem<SROWS>();
   CK(cudaFuncSetAttribute(krowsp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smrp));
   auto krowst = k_corr_rows_t<SROWS, TTHREADS, TMINCTAS>;
-  auto kcolst = k_corr_cols_s<SCOLS, kMulti, 128, 4, false>;
+  auto kcolst = k_corr_cols_s<SCOLS, kMulti, CTHREADS, CMINCTAS, CSPLIT>;
   CK(cudaFuncSetAttribute(kcolst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)hp.N1 * kTileW * (sizeof(float2) + (kMulti ? sizeof(float) : 0)))));
   const size_t smrt = rows_t_smem<SROWS>();
   CK(cudaFuncSetAttribute(krowst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smrt));
@@ -143,8 +148,8 @@ int main(int argc, char** argv) {
   time("cols (spec)", [&] { run_cols(0); });
   time("cols (pipelined)", [&] { run_colsp(0); });
   time("rows (small CTAs)", [&] { run_rowst(0, scr); });
-  time("cols (small CTAs)", [&] { kcolst<<<dim3(ntiles, U), 128, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
-  time("rows+cols (small CTAs)", [&] { run_rowst(0, scr); kcolst<<<dim3(ntiles, U), 128, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
+  time("cols (small CTAs)", [&] { kcolst<<<dim3(ntiles, U), CTHREADS, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
+  time("rows+cols (small CTAs)", [&] { run_rowst(0, scr); kcolst<<<dim3(ntiles, U), CTHREADS, smc, 0>>>(dp, scr, R, B, Dc, 0, 0, N, scale, ntiles, pa, nullptr); });
   time("rows (pipelined)", [&] { run_rowsp(0, scr); });
   time("rows+cols (both pipelined)", [&] { run_rowsp(0, scr); run_colsp(0); });
   time("rows+cols (spec)", [&] { run_rows(0); run_cols(0); });
