@@ -47,6 +47,12 @@ struct Sub {
 constexpr bool is_split_radix(int R) { return R == 31; }
 // butterflies a thread keeps in flight per loop trip: small radices need several for ILP
 constexpr int stage_unroll(int R) { return R <= 5 ? 4 : (R <= 10 ? 2 : 1); }
+// butterflies whose global loads the columns kernel's first stage keeps in flight per thread
+#ifdef GNSSACQ_COLS_LOAD_UNROLL
+constexpr int cols_load_unroll(int) { return GNSSACQ_COLS_LOAD_UNROLL; }      // A/B builds of tools/microbench only
+#else
+constexpr int cols_load_unroll(int R) { return stage_unroll(R); }
+#endif
 
 // ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs
 template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
@@ -400,7 +406,7 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
     {
       constexpr int R = S::radix(NS - 1), nbf = N1 / R;
       if (tc < ncols) {
-#pragma unroll stage_unroll(R)
+#pragma unroll (cols_load_unroll(R))
         for (int bf = tb; bf < nbf; bf += nb) {
           float2 v[R];
 #pragma unroll
