@@ -191,11 +191,12 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
 }
 
 // Choose N = N1*N2 with both factors tile-sized and as square as possible.
-// use_pfa(sub-plan, which): whether the kernels that will run sub-transform `which` (1: length N1,
-// 2: length N2) are the twiddle-free prime-factor ones (asked only for coprime schedules).
+// use_pfa(plan, which): whether the kernels that will run sub-transform `which` (1: length N1,
+// 2: length N2) are the twiddle-free prime-factor ones (asked only for coprime schedules; the plan
+// carries both radix schedules at that point, no tables yet).
 inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, unsigned long long disabled = 0,
                       const std::vector<int>* sched1 = nullptr, const std::vector<int>* sched2 = nullptr,
-                      const std::function<bool(const HostSubPlan&, int)>* use_pfa = nullptr) {
+                      const std::function<bool(const HostPlan&, int)>* use_pfa = nullptr) {
   pl = HostPlan();
   pl.N = N;
   if (N < 4) { err = "FFT length must be >= 4"; return false; }
@@ -236,8 +237,8 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
   }
   if (!make_subplan(pl.N1, pl.s1, disabled, sched1) || !make_subplan(pl.N2, pl.s2, disabled, sched2)) { err = "unsupported factorisation"; return false; }
   if (use_pfa && pl.large) {
-    if (coprime_schedule(pl.s1.radix) && (*use_pfa)(pl.s1, 1)) set_pfa(pl.s1);
-    if (coprime_schedule(pl.s2.radix) && (*use_pfa)(pl.s2, 2)) set_pfa(pl.s2);
+    if (coprime_schedule(pl.s1.radix) && (*use_pfa)(pl, 1)) set_pfa(pl.s1);
+    if (coprime_schedule(pl.s2.radix) && (*use_pfa)(pl, 2)) set_pfa(pl.s2);
   }
   for (int r : pl.s1.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));

@@ -140,18 +140,29 @@ int upload_plan(gnssacq* h, int N) {
   // touches that sub-transform is a plan-specialised one (they carry the index maps; the generic
   // runtime-planned kernels are Cooley-Tukey only).
   const bool spec = h->use_spec;
-  const std::function<bool(const HostSubPlan&, int)> use_pfa = [spec](const HostSubPlan& hs, int which) {
+  const std::function<bool(const HostPlan&, int)> use_pfa = [spec](const HostPlan& hpl, int which) {
     if (!spec) return false;
-    SubPlan sp{};                         // schedule only: the twiddle tables do not exist yet
-    sp.F = hs.F;
-    sp.ns = (int)hs.radix.size();
-    for (int j = 0; j < kMaxStages; ++j) {
-      sp.radix[j] = j < sp.ns ? hs.radix[j] : 1;
-      sp.m[j] = j < sp.ns ? hs.m[j] : 1;
+    auto schedule_of = [](const HostSubPlan& hs, bool pfa) {      // schedule only: the twiddle tables do not exist yet
+      SubPlan sp{};
+      sp.F = hs.F;
+      sp.ns = (int)hs.radix.size();
+      for (int j = 0; j < kMaxStages; ++j) {
+        sp.radix[j] = j < sp.ns ? hs.radix[j] : 1;
+        sp.m[j] = j < sp.ns ? hs.m[j] : 1;
+      }
+      sp.pfa = pfa ? 1 : 0;
+      return sp;
+    };
+    if (which == 1) {
+      const SubPlan s1 = schedule_of(hpl.s1, true);
+      return find_cols_kernel(s1, false) && find_cols_kernel(s1, true) && find_fwd_cols_kernel(s1, 0) && find_fwd_cols_kernel(s1, 1);
     }
-    sp.pfa = 1;
-    return which == 1 ? (find_cols_kernel(sp, false) && find_cols_kernel(sp, true) && find_fwd_cols_kernel(sp, 0) && find_fwd_cols_kernel(sp, 1))
-                      : (find_rows_kernel(sp) && find_fwd_rows_kernel(sp));
+    // The columns of the inverse are tile positions of the length-N2 transform: only the specialised
+    // columns kernels translate them back to lags (n2_of_pos), so they must exist for s1 as it will
+    // run (prime-factor or not — s1 has been decided by now).
+    const SubPlan s1 = schedule_of(hpl.s1, hpl.s1.pfa);
+    const SubPlan s2 = schedule_of(hpl.s2, true);
+    return find_rows_kernel(s2) && find_fwd_rows_kernel(s2) && find_cols_kernel(s1, false) && find_cols_kernel(s1, true);
   };
   if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1], &use_pfa)) return fail(GNSSACQ_EINVAL, err);
   h->plan_dirty = false;

@@ -222,8 +222,9 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
   // plans: n1 = (n1_of_pos[i] + q * F/R0) mod F (one table read per butterfly, outside the
   // peak-search branch: with ~46 outputs per thread and tile, some lane of a warp takes that
   // branch for most outputs, so its body must stay a few integer instructions);
-  // Cooley-Tukey plans: n1 = pos, n2 = column.
-  const int lagc = (S::kPfa && tc < ncols) ? __ldg(&pl.n2_of_pos[lag0]) : lag0;
+  // Cooley-Tukey plans: n1 = pos; n2 = n2_of_pos[column] (the identity unless the rows transform is prime-factor).
+  // the column map belongs to the length-N2 transform, whatever S (the length-N1 schedule) is: always through the table
+  const int lagc = tc < ncols ? __ldg(&pl.n2_of_pos[lag0]) : 0;
   auto n1_base = [&](int i) -> int { if constexpr (S::kPfa) return __ldg(&pl.n1_of_pos[i]); else return i; };
   auto n1_of = [&](int n1i, int q) -> int {
     if constexpr (S::kPfa) { const int n = n1i + q * (S::F / R0); return n >= S::F ? n - S::F : n; }

@@ -180,3 +180,11 @@ def test_large_163680_prime_factor_31x12(eng):
     twiddle-free prime-factor schedules (small-CTA kernels, radix 12 in registers)."""
     info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
     assert info['N1'] == 372 and info['N2'] == 440 and eng.kernel_variant() == 27
+
+
+@pytest.mark.slow
+def test_large_mixed_prime_factor_and_generic(eng):
+    """32736 = 186 x 176: the columns transform (31*6) is a specialised prime-factor one, the rows
+    transform (11*16) has no specialisation and runs the generic Cooley-Tukey kernels."""
+    info = _case(eng, 32736, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1)
+    assert info['N1'] == 186 and info['N2'] == 176 and eng.kernel_variant() == (2 | 8)

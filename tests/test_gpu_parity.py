@@ -51,6 +51,8 @@ ENGINE_CASES = [
     ('D-l2cm-2x81920', 10230, 4096000.0, 81920, True, False, False, 1, (-40, 40, 20), 2, None),
     ('cfg2-163680-10ms', 1023, 16368000.0, 163680, False, False, True, 1, (-500, 500, 250), 3, 16368),
     ('cfg4-native-2x25000', 10230, 25000000.0, 25000, True, False, False, 4, (-400, 400, 200), 2, None),
+    # 32736 = 186 x 176: prime-factor specialised columns transform (31*6) with a generic Cooley-Tukey rows transform (11*16)
+    ('mixed-32736-2ms', 1023, 16368000.0, 32736, False, False, True, 2, (-500, 500, 250), 2, None),
 ]
 
 

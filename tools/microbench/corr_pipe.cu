@@ -52,9 +52,9 @@ int main(int argc, char** argv) {
   const int reps = argc > 2 ? atoi(argv[2]) : 40;
   HostPlan hp; std::string err;
   #ifdef GNSSACQ_NO_PFA
-  const std::function<bool(const HostSubPlan&, int)> use_pfa = [](const HostSubPlan&, int) { return false; };
+  const std::function<bool(const HostPlan&, int)> use_pfa = [](const HostPlan&, int) { return false; };
 #else
-  const std::function<bool(const HostSubPlan&, int)> use_pfa = [](const HostSubPlan&, int) { return true; };
+  const std::function<bool(const HostPlan&, int)> use_pfa = [](const HostPlan&, int) { return true; };
 #endif
 #ifdef SCHED1
   const std::vector<int> sched1 = {SCHED1, SCHED1B};
