@@ -324,7 +324,11 @@ def main():
                      'kernel': 'correlate stage = rows kernel k_corr_rows_t + columns kernel k_corr_cols_s (one logical fused correlate; chunks of units alternate over two streams, so the stage is timed as one span)',
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                      'kernel_ms_per_step': corr_ms / K, 'kernel_launches_per_step': corr_launches / K,
-                     'stage_ms_per_step': {k: v[0] / K for k, v in stages.items()}},
+                     'stage_ms_per_step': {k: v[0] / K for k, v in stages.items()},
+                     # the HBM roofline is the one BASELINE.json asks for; what actually binds (ncu, profiles/README.md):
+                     'binding': 'latency / L2 traffic, not HBM: issue slots ~39 % active, FMA pipe ~31 %, DRAM ~12 % busy; '
+                                '~40 B per cell-block through L2 (X, C, four-step twiddle, scratch out and back) '
+                                'against 16 B algorithmic (profiles/r02f_corr_ncu_summary.txt)'},
     }
     if not args.no_cpu_baseline:
         v, dt, info = cpu_baseline(x.astype(np.complex128), list(range(1, 33)), bins[:D_PER_GPU])
