@@ -182,6 +182,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     sig, x, rep, sats = make_inputs()
