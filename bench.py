@@ -182,9 +182,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and =WARN; stdout carries the
+        # JSON line only, so anything below INFO is switched off (INFO / TRACE, if asked for, are kept)
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE', 'ABORT'):
+            os.environ['NCCL_DEBUG'] = 'NONE'
         dist.init_process_group('nccl', device_id=dev)
 
     sig, x, rep, sats = make_inputs()
