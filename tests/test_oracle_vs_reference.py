@@ -132,3 +132,15 @@ def test_oracle_matches_reference_glonass_p_search(band, step):
     want = ref_search(x, chan, doppler, ca_phase, ms)
     got = orc.search_glonass_p(x, chips, fs, step, chan, doppler, ca_phase, ms)
     assert got == tuple(want) and got[1] == 421, (got, want)
+
+
+def test_serial_script_constants_match_reference_sources():
+    """The constants acquire_serial.py hard-codes are the ones in the reference scripts."""
+    import os
+    src = {s: open(os.path.join(ref_lift.REF, 'acquire-%s.py' % s)).read() for s in ('gps-l2cl', 'glonass-l1-p', 'glonass-l2-p')}
+    for token in ('range(75)', 'ms//20', 'int(fs*0.020)', '(k+block)*10230+l2cm_code_phase', "default=40"):
+        assert token in src['gps-l2cl'], token
+    for s, step in (('glonass-l1-p', '562500'), ('glonass-l2-p', '437500')):
+        for token in ('range(1000)', 'ms//4', 'int(fs*0.004)', '5110*k + 10*ca_code_phase', 'cp += n*incr', '5110000.0/fs',
+                      step + '*chan+doppler', "default=80"):
+            assert token in src[s], (s, token)
