@@ -241,6 +241,7 @@ template <int R1, int R2> struct DftPFA {
 template <int R1, int R2> struct DftCT {
   static __device__ __forceinline__ void run(float2* v) {
     constexpr int R = R1 * R2;
+    constexpr float kH = 0.70710678118654752440f;
     float2 t[R];
     static_for<0, R2>([&](auto N2) {
       constexpr int n2 = decltype(N2)::value;
@@ -250,10 +251,18 @@ template <int R1, int R2> struct DftCT {
       Dft<R1>::run(u);
       static_for<0, R1>([&](auto K1) {
         constexpr int k1 = decltype(K1)::value;
-        if constexpr ((k1 * n2) % R == 0) t[k1 * R2 + n2] = u[k1];
+        constexpr int e = (k1 * n2) % R;                  // u *= W_R^e = exp(-2*pi*i*e/R)
+        if constexpr (e == 0) t[k1 * R2 + n2] = u[k1];
+        else if constexpr (4 * e == R) t[k1 * R2 + n2] = cmul_mi(u[k1]);
+        else if constexpr (2 * e == R) t[k1 * R2 + n2] = make_float2(-u[k1].x, -u[k1].y);
+        else if constexpr (4 * e == 3 * R) t[k1 * R2 + n2] = make_float2(-u[k1].y, u[k1].x);
+        else if constexpr (8 * e == R) t[k1 * R2 + n2] = make_float2(kH * (u[k1].x + u[k1].y), kH * (u[k1].y - u[k1].x));
+        else if constexpr (8 * e == 3 * R) t[k1 * R2 + n2] = make_float2(kH * (u[k1].y - u[k1].x), -kH * (u[k1].x + u[k1].y));
+        else if constexpr (8 * e == 5 * R) t[k1 * R2 + n2] = make_float2(-kH * (u[k1].x + u[k1].y), kH * (u[k1].x - u[k1].y));
+        else if constexpr (8 * e == 7 * R) t[k1 * R2 + n2] = make_float2(kH * (u[k1].x - u[k1].y), kH * (u[k1].x + u[k1].y));
         else {
-          constexpr float wc = kTrig<R>.c[(k1 * n2) % R];
-          constexpr float ws = kTrig<R>.s[(k1 * n2) % R];
+          constexpr float wc = kTrig<R>.c[e];
+          constexpr float ws = kTrig<R>.s[e];
           t[k1 * R2 + n2] = cmul(u[k1], make_float2(wc, -ws));
         }
       });
@@ -270,6 +279,9 @@ template <int R1, int R2> struct DftCT {
   }
 };
 
+// 32 = 4 x 8 Cooley-Tukey with compile-time twiddles: lets 480 = 15 * 32 and 352 = 11 * 32 run as
+// two-stage prime-factor tile transforms (one shared-memory pass).
+template <> struct Dft<32> : DftCT<4, 8> {};
 template <> struct Dft<6> : DftPFA<2, 3> {};
 template <> struct Dft<10> : DftPFA<2, 5> {};
 template <> struct Dft<12> : DftPFA<4, 3> {};
@@ -445,11 +457,11 @@ __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F,
 
 // Radix classes: kernels are instantiated per class so that power-of-two plans are not
 // register-allocated for the 31-point butterfly. 0: {2,4,8,16}; 1: + {3,5,6,9,10,12,15,20,25};
-// 2: + {7,11,13,22,31}.
+// 2: + {7,11,13,22,31,32}.
 constexpr int kNumRadixClasses = 3;
 __host__ __device__ constexpr int radix_class_of(int R) {
   return (R == 2 || R == 4 || R == 8 || R == 16) ? 0
-       : ((R == 3 || R == 5 || R == 6 || R == 9 || R == 10 || R == 12 || R == 15 || R == 20 || R == 25) ? 1 : 2);
+       : ((R == 3 || R == 5 || R == 6 || R == 9 || R == 10 || R == 12 || R == 15 || R == 20 || R == 25) ? 1 : 2);   // 32 -> 2
 }
 // prime factors the planner accepts
 __host__ __device__ constexpr bool radix_supported(int R) {
@@ -484,6 +496,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float2* tile, int WP, int 
                 case 13: stage_tile<13, INV>(tile, WP, ncols, F, m, tw); break;
                 case 22: stage_tile<22, INV>(tile, WP, ncols, F, m, tw); break;
                 case 31: stage_tile_split<31, INV>(tile, ncols, F, m, tw, WP); break;
+                case 32: stage_tile<32, INV>(tile, WP, ncols, F, m, tw); break;
                 default: break;   // the host planner never emits other radices
               }
             }

@@ -66,7 +66,28 @@ struct HostPlan {
   std::vector<float2> twm;           // twm[p1*N2 + n2] = exp(-2 pi i k1(p1) n2 / N)       (forward: columns are natural n2)
   std::vector<float2> twm_inv;       // twm_inv[p1*N2 + p2] = exp(-2 pi i k1(p1) n2(p2) / N) (inverse: columns are positions);
                                      // empty when s2 is not a prime-factor transform (then equal to twm)
+  // Coprime split (gcd(N1, N2) == 1): the four-step itself runs in Good-Thomas form. Time sample
+  // n sits at (n1, n2) with n = (N2*n1 + N1*n2) mod N, frequency k at (k mod N1, k mod N2), and
+  // W_N^(nk) = W_N1^(n1 k1) * W_N2^(n2 k2): a plain two-dimensional DFT, so the twiddle tables
+  // above are not built and no kernel multiplies by them. Memory stays row-major in
+  // (m, b) = (n div N2, n mod N2); the index maps below place a sample in its tile.
+  bool gt = false;
+  std::vector<int> fpos1;            // [N1] a = n mod N1 -> tile position of the length-N1 transform that takes the sample
+  std::vector<int> fpos2;            // [N2] b = n mod N2 -> tile position of the length-N2 transform
+  std::vector<int> col_lag;          // [N2] lag contribution of inverse column position q2: N1 * n2(q2) (non-gt: n2(q2))
 };
+
+inline int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// Preferred coprime split of the lengths measured on B200 (N1 carries the radix-31 factor: the
+// columns kernel fuses that butterfly with the magnitude / peak epilogue).
+inline int measured_gt_n1(int N) {
+  switch (N) {
+    case 163680: return 341;         // 341 = 31*11, 480 = 15*32
+    case 61380: return 279;          // 279 = 31*9, 220 = 11*20
+    default: return 0;
+  }
+}
 
 inline std::vector<int> prime_factors(int n) {
   std::vector<int> f;
@@ -111,7 +132,9 @@ inline bool make_subplan(int F, HostSubPlan& sp, unsigned long long disabled = 0
   // schedules measured faster than the rule above (tools/ab_sched.py, bench_configs.py)
   // 372 = 31 * 12: with the twiddle-free prime-factor form the in-register radix 12 = 4 x 3 saves a
   // shared-memory pass over 31 * 3 * 4 (columns kernel 24.7 -> 22.6 us per 32 units of 163680)
-  static const std::vector<std::vector<int>> kMeasured = {{10, 20}, {10, 25}, {11, 20}, {31, 12}};
+  // 480 = 15 * 32 and 352 = 11 * 32: two-stage prime-factor schedules with the in-register radix 32
+  // (radix 32 is not part of the general search: it would re-plan the tuned power-of-two lengths)
+  static const std::vector<std::vector<int>> kMeasured = {{10, 20}, {10, 25}, {11, 20}, {31, 12}, {15, 32}, {11, 32}};
   if (!disabled)
     for (const auto& m : kMeasured) {
       long long prod = 1;
@@ -196,7 +219,7 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
 // carries both radix schedules at that point, no tables yet).
 inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, unsigned long long disabled = 0,
                       const std::vector<int>* sched1 = nullptr, const std::vector<int>* sched2 = nullptr,
-                      const std::function<bool(const HostPlan&, int)>* use_pfa = nullptr) {
+                      const std::function<bool(const HostPlan&, int)>* use_pfa = nullptr, bool allow_gt = false) {
   pl = HostPlan();
   pl.N = N;
   if (N < 4) { err = "FFT length must be >= 4"; return false; }
@@ -215,6 +238,10 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
   // magnitude/peak epilogue, measured 5-9 % faster for 61380 = 279 x 220 and 30690 = 186 x 165.
   pl.N1 = best; pl.N2 = N / best;
   if (pl.N1 > 1 && pl.N2 % 31 == 0 && pl.N1 % 31 != 0) std::swap(pl.N1, pl.N2);
+  if (allow_gt && force_n1 == 0 && N > kMidMax) {
+    const int g = measured_gt_n1(N);
+    if (g > 1 && N % g == 0 && gcd_int(g, N / g) == 1) { pl.N1 = g; pl.N2 = N / g; }
+  }
   if (force_n1 > 1 && N % force_n1 == 0 && force_n1 <= kMaxSub && N / force_n1 <= kMaxSub && N / force_n1 > 1) {
     pl.N1 = force_n1; pl.N2 = N / force_n1;
   }
@@ -236,6 +263,7 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
     }
   }
   if (!make_subplan(pl.N1, pl.s1, disabled, sched1) || !make_subplan(pl.N2, pl.s2, disabled, sched2)) { err = "unsupported factorisation"; return false; }
+  pl.gt = allow_gt && pl.large && gcd_int(pl.N1, pl.N2) == 1;
   if (use_pfa && pl.large) {
     if (coprime_schedule(pl.s1.radix) && (*use_pfa)(pl, 1)) set_pfa(pl.s1);
     if (coprime_schedule(pl.s2.radix) && (*use_pfa)(pl, 2)) set_pfa(pl.s2);
@@ -244,6 +272,17 @@ inline bool make_plan(int N, HostPlan& pl, std::string& err, int force_n1 = 0, u
   for (int r : pl.s2.radix) pl.rclass = std::max(pl.rclass, radix_class_of(r));
   pl.tw1 = unit_roots(pl.s1);
   pl.tw2 = unit_roots(pl.s2);
+  pl.col_lag.resize(pl.N2);
+  for (int q2 = 0; q2 < pl.N2; ++q2) pl.col_lag[q2] = (pl.gt ? pl.N1 : 1) * pl.s2.n_of_pos[q2];
+  if (pl.gt) {
+    const int inv2 = modinv(pl.N2 % pl.N1, pl.N1), inv1 = modinv(pl.N1 % pl.N2, pl.N2);
+    pl.fpos1.resize(pl.N1);
+    pl.fpos2.resize(pl.N2);
+    for (int a = 0; a < pl.N1; ++a) pl.fpos1[a] = pl.s1.pos_of_n[(int)(((long long)a * inv2) % pl.N1)];
+    for (int b = 0; b < pl.N2; ++b) pl.fpos2[b] = pl.s2.pos_of_n[(int)(((long long)b * inv1) % pl.N2)];
+    pl.twm.assign(1, make_float2(1.f, 0.f));       // never read
+    return true;
+  }
   pl.twm.resize((size_t)N);
   for (int p1 = 0; p1 < pl.N1; ++p1) {
     const long long k1 = pl.s1.freq_of_pos[p1];

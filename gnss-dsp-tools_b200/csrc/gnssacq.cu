@@ -82,6 +82,7 @@ struct gnssacq {
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
+  bool use_gt = true;                 // coprime four-step splits (no twiddle pass) for the lengths that have one
   int small_ctas = 3;                 // bit 0: 8-row / 128-160-thread rows kernel, bit 1: 128-thread columns kernel
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
   unsigned long long disabled_radices = 0;   // tuning: stage radices the planner may not use
@@ -162,9 +163,9 @@ int upload_plan(gnssacq* h, int N) {
     // run (prime-factor or not — s1 has been decided by now).
     const SubPlan s1 = schedule_of(hpl.s1, hpl.s1.pfa);
     const SubPlan s2 = schedule_of(hpl.s2, true);
-    return find_rows_kernel(s2) && find_fwd_rows_kernel(s2) && find_cols_kernel(s1, false) && find_cols_kernel(s1, true);
+    return find_rows_kernel(s2, hpl.gt) && find_fwd_rows_kernel(s2) && find_cols_kernel(s1, false) && find_cols_kernel(s1, true);
   };
-  if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1], &use_pfa)) return fail(GNSSACQ_EINVAL, err);
+  if (!make_plan(N, hp, err, h->force_n1, h->disabled_radices, &h->forced_sched[0], &h->forced_sched[1], &use_pfa, h->use_gt)) return fail(GNSSACQ_EINVAL, err);
   h->plan_dirty = false;
   if (int rc = h->d_tw1.ensure(hp.tw1.size() * sizeof(float2))) return rc;
   if (int rc = h->d_tw2.ensure(hp.tw2.size() * sizeof(float2))) return rc;
@@ -181,6 +182,9 @@ int upload_plan(gnssacq* h, int N) {
   maps.insert(maps.end(), hp.s1.n_of_pos.begin(), hp.s1.n_of_pos.end());
   maps.insert(maps.end(), hp.s2.n_of_pos.begin(), hp.s2.n_of_pos.end());
   maps.insert(maps.end(), hp.s2.pos_of_n.begin(), hp.s2.pos_of_n.end());
+  maps.insert(maps.end(), hp.col_lag.begin(), hp.col_lag.end());
+  maps.insert(maps.end(), hp.fpos1.begin(), hp.fpos1.end());          // empty unless hp.gt
+  maps.insert(maps.end(), hp.fpos2.begin(), hp.fpos2.end());
   if (int rc = h->d_maps.ensure(maps.size() * sizeof(int))) return rc;
   CU(cudaMemcpyAsync(h->d_maps.p, maps.data(), maps.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (hp.cube) {
@@ -200,6 +204,10 @@ int upload_plan(gnssacq* h, int N) {
   h->dp.n1_of_pos = h->d_maps.as<int>();
   h->dp.n2_of_pos = h->d_maps.as<int>() + hp.N1;
   h->dp.pos2_of_n = h->d_maps.as<int>() + hp.N1 + hp.N2;
+  h->dp.col_lag = h->d_maps.as<int>() + hp.N1 + 2 * hp.N2;
+  h->dp.gt = hp.gt ? 1 : 0;
+  h->dp.fpos1 = h->d_maps.as<int>() + hp.N1 + 3 * hp.N2;
+  h->dp.fpos2 = h->dp.fpos1 + hp.N1;
   h->hp = std::move(hp);
   return 0;
 }
@@ -314,11 +322,12 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
     } else {
       size_t smr = rows_smem(p);
       const size_t smc = cols_smem(p, B > 1);
-      corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2) : nullptr;
+      const bool gt = p.gt != 0;
+      corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2, gt) : nullptr;
       corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1, B > 1) : nullptr;
       int tr = kThreads, tcn = kThreads, row_tile = kTileW;
       if (h->use_spec && (h->small_ctas & 1)) {
-        const RowsSmall rs = find_rows_small(p.s2);
+        const RowsSmall rs = find_rows_small(p.s2, gt);
         if (rs.fn) { kr = rs.fn; tr = rs.threads; smr = rs.smem; row_tile = kRowsSmallTile; }
       }
       if (h->use_spec && (h->small_ctas & 2)) {
@@ -639,6 +648,11 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
     h->use_spec = value != 0;
     return 0;
   }
+  if (std::string(name) == "gt_split") {                // changes the spectrum layout: replicas must be set again
+    if (h->use_gt != (value != 0)) { h->R = 0; h->plan_dirty = true; }
+    h->use_gt = value != 0;
+    return 0;
+  }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
   if (std::string(name) == "small_ctas") { h->small_ctas = value; return 0; }
   if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
@@ -801,7 +815,8 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
   if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
-  return (find_rows_kernel(h->dp.s2) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0);
+  return (find_rows_kernel(h->dp.s2, h->hp.gt) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0) |
+         (h->hp.gt ? 32 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

@@ -25,6 +25,14 @@ struct DevPlan {
   const int* n1_of_pos;  // time index n1 held at position p1 of the length-N1 tile (identity unless s1.pfa)
   const int* n2_of_pos;  // likewise for the length-N2 tile
   const int* pos2_of_n;  // inverse of n2_of_pos
+  // Coprime split (fft_plan.h, HostPlan::gt): no four-step twiddles; sample n = m*N2 + b goes to tile
+  // position fpos1[n mod N1] of column b, a stored row goes through fpos2[b], and the lag of inverse
+  // output (n1, column q2) is (n1*N2 + col_lag[q2]) mod N. col_lag is valid for every plan
+  // (n2_of_pos when gt == 0).
+  int gt;
+  const int* fpos1;
+  const int* fpos2;
+  const int* col_lag;
 };
 
 // Per-(replica, doppler, tile) partial result of the correlate kernel.
@@ -215,15 +223,18 @@ k_fwd_cols(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ r
   if (SRC == 0) { const int d = t / B, b = t - d * B; base = (long long)b * stride; f = freq[d]; }
   else { base = (long long)t * N; }
   if (tc < ncols)
-    for (int n1 = tb; n1 < N1; n1 += nb)
-      tile[n1 * kTileW + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n1 * N2 + col0 + tc);
+    for (int n1 = tb; n1 < N1; n1 += nb) {
+      const int n = n1 * N2 + col0 + tc;
+      const int row = pl.gt ? __ldg(&pl.fpos1[n % N1]) : n1;
+      tile[row * kTileW + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n);
+    }
   __syncthreads();
   subfft_tile<RC, false>(tile, kTileW, ncols, pl.s1);
   float2* out = X + (long long)t * N;
   if (tc < ncols)
     for (int p1 = tb; p1 < N1; p1 += nb) {
       const int g = p1 * N2 + col0 + tc;
-      out[g] = cmul(tile[p1 * kTileW + tc], __ldg(&pl.twm[g]));
+      out[g] = pl.gt ? tile[p1 * kTileW + tc] : cmul(tile[p1 * kTileW + tc], __ldg(&pl.twm[g]));
     }
 }
 
@@ -239,7 +250,7 @@ k_fwd_rows(DevPlan pl, float2* __restrict__ X) {
   float2* Xt = X + (long long)blockIdx.y * N;
   for (int c = tb; c < nrows; c += nb)
     for (int e = tc; e < N2; e += kTW)
-      tile[e * kRowPitch + c] = Xt[(row0 + c) * N2 + e];
+      tile[(pl.gt ? __ldg(&pl.fpos2[e]) : e) * kRowPitch + c] = Xt[(row0 + c) * N2 + e];
   __syncthreads();
   subfft_tile<RC, false>(tile, kRowPitch, nrows, pl.s2);
   for (int c = tb; c < nrows; c += nb)
@@ -273,7 +284,7 @@ k_corr_rows(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__
   for (int c = tb; c < nrows; c += nb)
     for (int e = tc; e < N2; e += kTW) {
       const int g = (row0 + c) * N2 + e;
-      out[g] = cmulc(tile[e * kRowPitch + c], __ldg(&pl.twm[g]));
+      out[g] = pl.gt ? tile[e * kRowPitch + c] : cmulc(tile[e * kRowPitch + c], __ldg(&pl.twm[g]));
     }
 }
 
@@ -304,7 +315,8 @@ k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D,
     if (tc < ncols)
       for (int n1 = tb; n1 < N1; n1 += nb) {
         const float2 v = tile[n1 * kTileW + tc];
-        const int lag = n1 * N2 + col0 + tc;
+        int lag = n1 * N2 + __ldg(&pl.col_lag[col0 + tc]);
+        if (lag >= N) lag -= N;
         float acc = __fsqrt_rn(v.x * v.x + v.y * v.y) * scale;
         if (b > 0) acc += qs[n1 * kTileW + tc];
         if (!last) { qs[n1 * kTileW + tc] = acc; }

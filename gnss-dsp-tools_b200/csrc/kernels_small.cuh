@@ -72,7 +72,7 @@ __device__ __forceinline__ void inv_stages_rows8(float2* tile, int nrows, const 
 // Last inverse stage of the rows transform (stage 0, stride m0 >= 16) fused with the conjugate
 // four-step twiddle and the store: lanes walk i (consecutive positions), so tile reads, twiddle
 // reads and global stores are contiguous. Prime-factor schedules have no stage twiddle here.
-template <class S, int PP, int THREADS>
+template <class S, int PP, int THREADS, bool GT = false>
 __device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, const DevPlan& pl, float2* __restrict__ out, int row0) {
   constexpr int N2 = S::F, R0 = S::radix(0), m0 = S::stride(0);
   static_assert(!is_split_radix(R0), "warp-pair radices belong to the columns transform");
@@ -92,7 +92,7 @@ __device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, 
     }
     inv_dft<R0>(v);
 #pragma unroll
-    for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
+    for (int q = 0; q < R0; ++q) out[g + q * m0] = GT ? v[q] : cmulc(v[q], __ldg(&twm[g + q * m0]));
   }
 }
 
@@ -104,7 +104,7 @@ __device__ __forceinline__ void rows8_last_stage(const float2* tile, int nrows, 
 template <class S> __host__ __device__ constexpr size_t rows_t_smem() {
   return (size_t)kRowsTile8 * rows8_pitch<S>() * sizeof(float2);
 }
-template <class S, int THREADS, int MINCTAS>
+template <class S, int THREADS, int MINCTAS, bool GT = false>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_rows_t(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
               int R_, int B, int u0, float2* __restrict__ scratch) {
@@ -139,7 +139,7 @@ k_corr_rows_t(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
     const int c = threadIdx.x & 7, tb = threadIdx.x >> 3;
     constexpr int nb = THREADS / 8;
     if (c < nrows) {
-#pragma unroll 2
+#pragma unroll (R >= 16 ? 1 : 2)
       for (int bf = tb; bf < nbf; bf += nb) {
         const int e0 = c * PP + bf * R;
         float2 v[R];
@@ -162,7 +162,7 @@ k_corr_rows_t(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
   }
   __syncthreads();
   inv_stages_rows8<S, NS - 2, PP, THREADS>(tile, nrows, pl.s2);
-  rows8_last_stage<S, PP, THREADS>(tile, nrows, pl, scratch + ((long long)ul * B + b) * N + (long long)row0 * N2, row0);
+  rows8_last_stage<S, PP, THREADS, GT>(tile, nrows, pl, scratch + ((long long)ul * B + b) * N + (long long)row0 * N2, row0);
 }
 
 

@@ -127,7 +127,7 @@ template <class S> __host__ __device__ constexpr size_t rows_spec_smem() { retur
 
 template <class S> __host__ __device__ constexpr int rows_min_ctas() { return rows_spec_smem<S>() * 3 <= 200 * 1024 ? 3 : 2; }
 
-template <class S>
+template <class S, bool GT = false>
 __global__ void __launch_bounds__(kThreads, rows_min_ctas<S>())
 k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C,
               int R_, int B, int u0, float2* __restrict__ scratch) {
@@ -176,14 +176,14 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
       inv_dft<R0>(v);
       const int g = c * N2 + i;
 #pragma unroll
-      for (int q = 0; q < R0; ++q) out[g + q * m0] = cmulc(v[q], __ldg(&twm[g + q * m0]));
+      for (int q = 0; q < R0; ++q) out[g + q * m0] = GT ? v[q] : cmulc(v[q], __ldg(&twm[g + q * m0]));
     }
   } else {
     inv_stage_smem<S, 0, 1, P>(tile, nrows, pl.s2.tw, pl.s2.tws_off[0]);
     for (int c = tb; c < nrows; c += nb)
       for (int e = tc; e < N2; e += kTW) {
         const int g = c * N2 + e;
-        out[g] = cmulc(tile[c * P + e], __ldg(&twm[g]));
+        out[g] = GT ? tile[c * P + e] : cmulc(tile[c * P + e], __ldg(&twm[g]));
       }
   }
 }
@@ -224,7 +224,9 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
   // branch for most outputs, so its body must stay a few integer instructions);
   // Cooley-Tukey plans: n1 = pos; n2 = n2_of_pos[column] (the identity unless the rows transform is prime-factor).
   // the column map belongs to the length-N2 transform, whatever S (the length-N1 schedule) is: always through the table
-  const int lagc = tc < ncols ? __ldg(&pl.n2_of_pos[lag0]) : 0;
+  const int lagc = tc < ncols ? __ldg(&pl.col_lag[lag0]) : 0;       // n2 of the column; N1 * n2 for a coprime split
+  const int Nfull = pl.N;
+  auto lag_of = [&](int n1) -> int { const int l = n1 * N2 + lagc; return l >= Nfull ? l - Nfull : l; };   // wraps only when pl.gt
   auto n1_base = [&](int i) -> int { if constexpr (S::kPfa) return __ldg(&pl.n1_of_pos[i]); else return i; };
   auto n1_of = [&](int n1i, int q) -> int {
     if constexpr (S::kPfa) { const int n = n1i + q * (S::F / R0); return n >= S::F ? n - S::F : n; }
@@ -263,14 +265,14 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         if (acc[t] >= best) {
-          const int lag = n1_of(n1i, qof(t)) * N2 + lagc;
+          const int lag = lag_of(n1_of(n1i, qof(t)));
           if (lag < n_lags && (acc[t] > best || lag < bestlag)) { best = acc[t]; bestlag = lag; }
         }
       }
     }
     if (dump) {
 #pragma unroll
-      for (int t = 0; t < NB; ++t) qd[n1_of(n1i, qof(t)) * N2 + lagc] = acc[t] * scale;
+      for (int t = 0; t < NB; ++t) qd[lag_of(n1_of(n1i, qof(t)))] = acc[t] * scale;
     }
   };
   // batch handler for prime_outputs_batched: pairs k0..k0+nk-1 -> outputs k and R0-k (|.| ignores the re/im swap)
@@ -496,7 +498,17 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
   // tile position p1 takes time sample n1_of_pos[p1] (identity unless the plan is prime-factor)
   auto n1_at = [&](int p1) -> int { if constexpr (S::kPfa) return __ldg(&pl.n1_of_pos[p1]); else return p1; };
-  if constexpr (is_split_radix(R0)) {
+  if (pl.gt) {
+    // coprime split: rows of memory are m = n div N2; sample n = m*N2 + b of column b belongs to
+    // the tile position fpos1[n mod N1] (a different row rotation per column, loads stay coalesced)
+    if (tc < ncols)
+      for (int m = tb; m < N1; m += nb) {
+        const int n = m * N2 + col0 + tc;
+        tile[__ldg(&pl.fpos1[n % N1]) * WP + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n);
+      }
+    __syncthreads();
+    fwd_stage_smem<S, 0, WP, 1>(tile, ncols, pl.s1.tw, pl.s1.tws_off[0]);
+  } else if constexpr (is_split_radix(R0)) {
     if (tc < ncols)
       for (int n1 = tb; n1 < N1; n1 += nb)
         tile[n1 * WP + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n1_at(n1) * N2 + col0 + tc);
@@ -529,6 +541,7 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
     constexpr int R = S::radix(NS - 1), nbf = N1 / R;
     float2* out = X + (long long)t * N + col0 + tc;
     const float2* twm = pl.twm + col0 + tc;
+    const bool gt = pl.gt != 0;
     if (tc < ncols) {
 #pragma unroll stage_unroll(R)
       for (int bf = tb; bf < nbf; bf += nb) {
@@ -537,7 +550,7 @@ k_fwd_cols_s(DevPlan pl, const float2* __restrict__ x, const float* __restrict__
         for (int q = 0; q < R; ++q) v[q] = tile[(bf * R + q) * WP + tc];
         Dft<R>::run(v);
 #pragma unroll
-        for (int q = 0; q < R; ++q) out[(bf * R + q) * N2] = cmul(v[q], __ldg(&twm[(bf * R + q) * N2]));
+        for (int q = 0; q < R; ++q) out[(bf * R + q) * N2] = gt ? v[q] : cmul(v[q], __ldg(&twm[(bf * R + q) * N2]));
       }
     }
   }
@@ -560,7 +573,8 @@ k_fwd_rows_s(DevPlan pl, float2* __restrict__ X) {
 #pragma unroll 8
     for (int e = tc; e < N2; e += kTW) {
       int pe = e;
-      if constexpr (S::kPfa) pe = __ldg(&pl.pos2_of_n[e]);
+      if (pl.gt) pe = __ldg(&pl.fpos2[e]);
+      else if constexpr (S::kPfa) pe = __ldg(&pl.pos2_of_n[e]);
       tile[c * P + pe] = Xt[c * N2 + e];
     }
   }
@@ -590,6 +604,8 @@ using S200 = Sub<200, 10, 20>;
 using S250 = Sub<250, 10, 25>;
 using S248 = Sub<248, 31, 8>;
 using S496 = Sub<496, 31, 16>;
+using S341 = Sub<341, 31, 11>;           // coprime split of 163680 = 341 x 480
+using S480 = Sub<480, 15, 32>;
 
 template <class S> inline bool schedule_matches(const SubPlan& sp) {
   if (sp.F != S::F || sp.ns != S::NS || (sp.pfa != 0) != S::kPfa) return false;

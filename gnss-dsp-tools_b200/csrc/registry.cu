@@ -8,7 +8,7 @@ namespace acq {
 
 #define COLS_LIST_0(T) T(S128) T(S256) T(S320) T(S165)
 #define COLS_LIST_1(T) T(S220) T(S372b) T(S200) T(S248)
-#define COLS_LIST_2(T) T(S496) T(S186) T(S279)
+#define COLS_LIST_2(T) T(S496) T(S186) T(S279) T(S341)
 
 corr_cols_fn find_cols_part0(const SubPlan&, bool);
 corr_cols_fn find_cols_part1(const SubPlan&, bool);
@@ -21,13 +21,13 @@ constexpr int kColsSmallThreads = 128;
 #if GNSSACQ_REG_PART == 0
 fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
 #define TRY(S) if (schedule_matches<S>(s1)) return src == 0 ? k_fwd_cols_s<S, 0> : k_fwd_cols_s<S, 1>;
-  TRY(S128) TRY(S256) TRY(S320) TRY(S165) TRY(S220) TRY(S372b) TRY(S200) TRY(S248) TRY(S496) TRY(S186) TRY(S279)
+  TRY(S128) TRY(S256) TRY(S320) TRY(S165) TRY(S220) TRY(S372b) TRY(S200) TRY(S248) TRY(S496) TRY(S186) TRY(S279) TRY(S341)
 #undef TRY
   return nullptr;
 }
 fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 #define TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
-  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220)
+  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220) TRY(S480)
 #undef TRY
   return nullptr;
 }
@@ -43,7 +43,13 @@ ColsSmall find_cols_small(const SubPlan& s1, bool multi) {
   return ColsSmall{f, f ? kColsSmallThreads : 0};
 }
 #elif GNSSACQ_REG_PART == 1
-corr_rows_fn find_rows_kernel(const SubPlan& s2) {
+corr_rows_fn find_rows_kernel(const SubPlan& s2, bool gt) {
+  if (gt) {                              // coprime splits (no four-step twiddle): the lengths that have one
+#define TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S, true>;
+    TRY(S220) TRY(S480)
+#undef TRY
+    return nullptr;
+  }
 #define TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S>;
   TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220)
 #undef TRY
@@ -52,8 +58,14 @@ corr_rows_fn find_rows_kernel(const SubPlan& s2) {
 // threads / CTAs per SM: enough registers for the widest in-register butterfly of the schedule.
 // Listed = measured faster than the 256-thread kernel on B200 (tools/bench_configs.py small_ctas=0..3,
 // profiles/README.md r02): 2-20 %; 256 = 16*16 lost 2-7 % and stays on the 256-thread kernel.
-RowsSmall find_rows_small(const SubPlan& s2) {
+RowsSmall find_rows_small(const SubPlan& s2, bool gt) {
   static_assert(kRowsSmallTile == kRowsTile8, "row tile");
+  if (gt) {
+#define TRY(S, T, C) if (schedule_matches<S>(s2)) return RowsSmall{k_corr_rows_t<S, T, C, true>, T, rows_t_smem<S>()};
+    TRY(S220, 128, 4) TRY(S480, 128, 4)
+#undef TRY
+    return RowsSmall{nullptr, 0, 0};
+  }
 #define TRY(S, T, C) if (schedule_matches<S>(s2)) return RowsSmall{k_corr_rows_t<S, T, C>, T, rows_t_smem<S>()};
   TRY(S440, 192, 5) TRY(S128, 128, 6) TRY(S512, 128, 6) TRY(S320, 128, 6) TRY(S220, 128, 4) TRY(S250, 128, 4)
 #undef TRY

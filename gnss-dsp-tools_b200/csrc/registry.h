@@ -15,7 +15,7 @@ typedef void (*fwd_rows_fn)(DevPlan, float2*);
 // 256-thread kernels (kernels_spec.cuh); nullptr when the schedule has no specialisation
 fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src);
 fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2);
-corr_rows_fn find_rows_kernel(const SubPlan& s2);
+corr_rows_fn find_rows_kernel(const SubPlan& s2, bool gt = false);   // gt: coprime split, no four-step twiddle
 corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi);
 
 // small-CTA kernels (kernels_small.cuh): rows grid = (ceil(N1/8), B, units) with `smem` bytes,
@@ -23,7 +23,7 @@ corr_cols_fn find_cols_kernel(const SubPlan& s1, bool multi);
 struct RowsSmall { corr_rows_fn fn; int threads; size_t smem; };
 struct ColsSmall { corr_cols_fn fn; int threads; };
 constexpr int kRowsSmallTile = 8;
-RowsSmall find_rows_small(const SubPlan& s2);
+RowsSmall find_rows_small(const SubPlan& s2, bool gt = false);
 ColsSmall find_cols_small(const SubPlan& s1, bool multi);
 
 }  // namespace acq

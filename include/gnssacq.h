@@ -143,7 +143,8 @@ int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle
 /* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =
  * specialised columns kernel; 4 = the 16x16x16 single-CTA kernels (N = 4096); 0 = generic
  * runtime-planned kernels; bit 3 / bit 4 = the length-N1 / length-N2 tile transform runs in its
- * twiddle-free prime-factor form (coprime radix schedule). Negative on error. */
+ * twiddle-free prime-factor form (coprime radix schedule); bit 5 = the four-step split itself
+ * is coprime (Good-Thomas: no twiddle pass between the two transforms). Negative on error. */
 int gnssacq_kernel_variant(gnssacq_t* h);
 int gnssacq_synchronize(gnssacq_t* h);
 /* Tuning switches, for tests and A/B measurements. "specialized_kernels" (default 1): use the
@@ -154,7 +155,10 @@ int gnssacq_synchronize(gnssacq_t* h);
  * every kernel back to back on the handle's stream (what per-kernel stage times need).
  * "small_ctas" (default 3): bit 0 = 8-row / 128-160-thread rows kernel, bit 1 = 128-thread
  * columns kernel with the radix-31 butterfly in one thread (4-7 CTAs per SM instead of 2-3;
- * bit-identical results); 0 = the 256-thread kernels. */
+ * bit-identical results); 0 = the 256-thread kernels.
+ * "gt_split" (default 1): lengths with a coprime split N = N1*N2 (163680 = 341 x 480,
+ * 61380 = 279 x 220) run the four-step in Good-Thomas form, without the twiddle pass; 0 keeps
+ * the Cooley-Tukey split. Replicas must be set again afterwards. */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Tuning: force the stage radices (forward order) of the length-N1 (which = 1) or length-N2
  * (which = 2) tile transform; ignored when their product does not match; n = 0 restores the

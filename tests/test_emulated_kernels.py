@@ -69,8 +69,9 @@ def test_large_pow2_padded(eng):
 def test_large_61380_like_l5(eng):
     info = _case(eng, 30690, True, False, False, 2, (-400, 400, 400), 30.69e6, nprn=1)
     assert info['large'] and info['N'] == 61380
-    # 279 = 31*9 and 220 = 11*20 are coprime schedules: both tile transforms run twiddle-free (prime-factor)
-    assert eng.kernel_variant() & 24 == 24
+    # 279 = 31*9 and 220 = 11*20 are coprime schedules: both tile transforms run twiddle-free (prime-factor),
+    # and gcd(279, 220) = 1: the four-step split is coprime too (no twiddle pass)
+    assert eng.kernel_variant() & 56 == 56
     # the generic Cooley-Tukey kernels must agree with the prime-factor ones
     eng.set_option('specialized_kernels', 0)
     try:
@@ -175,11 +176,36 @@ def test_serial_searches_match_oracle(eng):
 
 
 @pytest.mark.slow
-def test_large_163680_prime_factor_31x12(eng):
-    """BASELINE config 2's transform: 163680 = 372 x 440 with 372 = 31*12 and 440 = 11*5*8, both
-    twiddle-free prime-factor schedules (small-CTA kernels, radix 12 in registers)."""
+def test_large_163680_coprime_split_341x480(eng):
+    """BASELINE config 2's transform as a coprime (Good-Thomas) four-step: 163680 = 341 x 480, no
+    twiddle pass; 341 = 31*11 and 480 = 15*32 are themselves twiddle-free two-stage schedules."""
     info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
-    assert info['N1'] == 372 and info['N2'] == 440 and eng.kernel_variant() == 27
+    assert info['N1'] == 341 and info['N2'] == 480 and eng.kernel_variant() == 59
+
+
+@pytest.mark.slow
+def test_large_163680_prime_factor_31x12(eng):
+    """The Cooley-Tukey split of the same length (gt_split = 0): 372 x 440 with 372 = 31*12 and
+    440 = 11*5*8, prime-factor tile transforms, four-step twiddles between them."""
+    eng.set_option('gt_split', 0)
+    try:
+        info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
+        assert info['N1'] == 372 and info['N2'] == 440 and eng.kernel_variant() == 27
+    finally:
+        eng.set_option('gt_split', 1)
+
+
+@pytest.mark.slow
+def test_coprime_split_generic_kernels_any_length(eng):
+    """A forced coprime split of a length without specialised kernels runs the generic kernels in
+    Good-Thomas form: 2 * 5 * 7 * 9 * 13 = 8190 -> 90 x 91... too short for a large plan, so 16380 = 130 x 126?
+    gcd(130, 126) = 2; 16380 = 4 * 9 * 5 * 7 * 13 = 180 x 91 (coprime)."""
+    eng.set_option('split_n1', 91)
+    try:
+        info = _case(eng, 16380, False, False, False, 2, (-300, 300, 300), 16.38e6, nprn=1)
+        assert info['N1'] == 91 and info['N2'] == 180 and eng.kernel_variant() & 32
+    finally:
+        eng.set_option('split_n1', 0)
 
 
 @pytest.mark.slow
