@@ -76,8 +76,6 @@ Arguments:
 
 def default_keys(name, sig):
     """--prn "" in the B2b scripts means every PRN the ICD defines (acquire-beidou-b2bi.py:71)."""
-    mod = acq.code_module(sig)
-    fn = getattr(mod, sig.module.split('.')[-1] + '_code')
     from . import _codegen
     return sorted(_codegen.memory_codes(sig.module).keys())
 

@@ -1,4 +1,6 @@
 """Pin the oracle restatement against the reference's own search() (build container only)."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -72,7 +74,7 @@ def synth(script, chips, key, ms, seed):
 def test_oracle_matches_reference_search(script, key, grid, ms):
     ref_search, ns = ref_lift.lift_search(script)
     chips, mod = ref_chips(ns, script, key)
-    x = synth(script, chips, key, ms, seed=hash(script) % 1000)
+    x = synth(script, chips, key, ms, seed=zlib.crc32(script.encode()) % 1000)   # stable across processes (hash() is salted)
     got = orc.search_script(script, x, chips, key, grid, ms)
     want = ref_search(x, key, grid, ms)
     assert got == tuple(want), (got, want)      # same arithmetic -> bit-identical float64
