@@ -16,6 +16,6 @@
 #define GNSSACQ_LAUNCH(kern, grid, block, smem, stream, ...) \
   kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define GNSSACQ_DYN_SMEM(type, name)                       \
-  extern __shared__ __align__(16) unsigned char gnssacq_dyn_smem_[]; \
+  extern __shared__ __align__(128) unsigned char gnssacq_dyn_smem_[]; \
   type* name = reinterpret_cast<type*>(gnssacq_dyn_smem_)
 #endif

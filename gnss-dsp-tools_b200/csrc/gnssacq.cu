@@ -6,6 +6,10 @@
 #include "preprocess.cuh"
 #include "kernels_cube.cuh"
 #include "bank.cuh"
+#include "async_copy.cuh"
+#ifndef GNSSACQ_EMU_BUILD
+#include <cuda.h>
+#endif
 
 #include <algorithm>
 #include <functional>
@@ -55,6 +59,7 @@ struct DevBuf {
 }  // namespace
 
 struct gnssacq {
+  static constexpr int kMaxLanes = 4;
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int64_t launches = 0;
@@ -83,6 +88,14 @@ struct gnssacq {
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
   bool use_spec = true;               // plan-specialised correlate kernels when one matches
   bool use_gt = true;                 // coprime four-step splits (no twiddle pass) for the lengths that have one
+  // copy-engine-fed correlate pair (kernels_v3.cuh) for coprime plans with two-stage schedules
+  bool use_v3 = true;
+  int v3_rows_variant = 0, v3_cols_variant = 0;      // tile shapes (registry.cu), A/B
+  int v3_rc = 0, v3_g = 0;                           // replicas x Doppler bins per launch (0 = automatic)
+  DevBuf d_v3tab;                                    // padded column table + tile origins
+  int v3tab_key[4] = {0, 0, 0, 0};                   // (N, RB, PB, CW) the table was built for
+  int v3_ntiles = 0;
+  struct LaneMap { TensorMap map; const void* base = nullptr; long long slots = 0; int NP = 0, CW = 0; } v3_map[kMaxLanes + 1];
   int small_ctas = 3;                 // bit 0: 8-row / 128-160-thread rows kernel, bit 1: 128-thread columns kernel
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
   unsigned long long disabled_radices = 0;   // tuning: stage radices the planner may not use
@@ -91,7 +104,6 @@ struct gnssacq {
   int force_uc = 0;                   // tuning: force the number of units per correlate launch
   bool overlap = true;                // large plans: alternate unit chunks over two streams so the
                                       // rows kernel of one chunk overlaps the columns kernel of the other
-  static constexpr int kMaxLanes = 4;
   int nlanes = 2;
   size_t scratch_bytes = kScratchBytes;   // total over all lanes
   size_t xchunk_bytes = kXChunkBytes;
@@ -296,6 +308,131 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
   });
 }
 
+// ---------------------------------------------------------------- copy-engine-fed pair (kernels_v3.cuh)
+struct V3Setup {
+  bool on = false;
+  RowsV3 r{};
+  ColsV3 c{};
+  int ntiles = 0, NP = 0, F1 = 0, F2 = 0;
+};
+
+// The pair runs when the plan is a coprime split and both tile transforms have an instantiation.
+V3Setup v3_setup(const gnssacq* h, bool multi) {
+  V3Setup v;
+  if (!h->use_v3 || !h->use_spec || !h->hp.large || !h->hp.gt || !h->hp.s1.pfa || !h->hp.s2.pfa) return v;
+  v.r = find_rows_v3(h->dp.s2, h->v3_rows_variant);
+  v.c = find_cols_v3(h->dp.s1, multi, h->v3_cols_variant);
+  if (!v.r.fn || !v.c.fn) return v;
+  if (v.r.smem > h->smem_optin || v.c.smem > h->smem_optin) return v;
+  v.NP = v.r.RA * v.r.PB;
+  v.ntiles = (v.r.RB % v.c.CW == 0) ? v.r.RA * (v.r.RB / v.c.CW) : (v.NP + v.c.CW - 1) / v.c.CW;
+  // tensor-map boxes are limited to 256 per dimension: N1 = F1 * F2 with the largest F1 <= 256
+  for (int f = 1; f <= 256 && f <= h->hp.N1; ++f)
+    if (h->hp.N1 % f == 0) v.F1 = f;
+  v.F2 = h->hp.N1 / v.F1;
+  if (v.F2 > 256) return v;
+  v.on = true;
+  return v;
+}
+
+// Padded column table (lag term of scratch column a'*PB + b', -1 for pad columns, -1 slack behind
+// the row for partly out-of-range tiles) followed by the tile origins.
+int v3_upload_tables(gnssacq* h, const V3Setup& v) {
+  const int key[4] = {h->hp.N, v.r.RB, v.r.PB, v.c.CW};
+  if (h->d_v3tab.p && std::equal(key, key + 4, h->v3tab_key) && h->v3_ntiles == v.ntiles) return 0;
+  const int ncol = v.NP + 2 * v.c.CW;
+  std::vector<int> tab((size_t)ncol + v.ntiles, -1);
+  for (int a = 0; a < v.r.RA; ++a)
+    for (int b = 0; b < v.r.RB; ++b) tab[(size_t)a * v.r.PB + b] = h->hp.col_lag[(size_t)a * v.r.RB + b];
+  const bool exact = v.r.RB % v.c.CW == 0;
+  const int per = exact ? v.r.RB / v.c.CW : 0;
+  for (int t = 0; t < v.ntiles; ++t) tab[(size_t)ncol + t] = exact ? (t / per) * v.r.PB + (t % per) * v.c.CW : t * v.c.CW;
+  if (int rc = h->d_v3tab.ensure(tab.size() * sizeof(int))) return rc;
+  CU(cudaMemcpyAsync(h->d_v3tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));            // `tab` is a local
+  std::copy(key, key + 4, h->v3tab_key);
+  h->v3_ntiles = v.ntiles;
+  return 0;
+}
+
+int v3_map_for(gnssacq* h, const V3Setup& v, int which, const void* base, long long slots) {
+  gnssacq::LaneMap& m = h->v3_map[which];
+  if (m.base == base && m.slots == slots && m.NP == v.NP && m.CW == v.c.CW) return 0;
+  const unsigned long long dims[3] = {(unsigned long long)v.NP, (unsigned long long)v.F1, (unsigned long long)v.F2 * (unsigned long long)slots};
+  const unsigned long long strides[2] = {(unsigned long long)v.NP * sizeof(float2), (unsigned long long)v.NP * sizeof(float2) * v.F1};
+  const unsigned box[3] = {(unsigned)v.c.CW, (unsigned)v.F1, (unsigned)v.F2};
+  const int rc = encode_tensor_map_3d_u64(&m.map, base, dims, strides, box);
+  if (rc != 0) return fail(GNSSACQ_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(rc));
+  m.base = base; m.slots = slots; m.NP = v.NP; m.CW = v.c.CW;
+  return 0;
+}
+
+// Chunk shape of the pair: replicas x Doppler bins per launch.
+void v3_chunk_shape(const gnssacq* h, int B, int dc, int& Rc, int& G) {
+  G = h->v3_g > 0 ? h->v3_g : std::max(1, 4 / B);
+  G = std::max(1, std::min(G, dc));
+  Rc = h->v3_rc > 0 ? h->v3_rc : 8;
+  Rc = std::max(1, std::min(Rc, h->R));
+}
+
+int correlate_chunk_v3(gnssacq* h, const V3Setup& v, int B, int D, int d0, int dc, int n_lags, float scale, float* d_qdump) {
+  const DevPlan& p = h->dp;
+  const int R = h->R;
+  int Rc, G;
+  v3_chunk_shape(h, B, dc, Rc, G);
+  const long long slots = (long long)Rc * G * B;
+  const size_t sbytes = (size_t)slots * p.N1 * v.NP * sizeof(float2);
+  const int nchunks = ((dc + G - 1) / G) * ((R + Rc - 1) / Rc);
+  const bool two_lanes = h->overlap && nchunks > 1;
+  if (int rc = v3_upload_tables(h, v)) return rc;
+  if (two_lanes) {
+    for (int l = 0; l < h->nlanes; ++l) {
+      if (int rc = h->d_scratch_lane[l].ensure(sbytes)) return rc;
+      if (int rc = v3_map_for(h, v, l, h->d_scratch_lane[l].p, slots)) return rc;
+    }
+  } else {
+    if (int rc = h->d_scratch.ensure(sbytes)) return rc;
+    if (int rc = v3_map_for(h, v, gnssacq::kMaxLanes, h->d_scratch.p, slots)) return rc;
+  }
+  if (int rc = allow_smem(h, v.r.fn, v.r.smem)) return rc;
+  if (int rc = allow_smem(h, v.c.fn, v.c.smem)) return rc;
+  DevPlan pv = p;                                    // the columns kernel indexes the padded column table
+  pv.col_lag = h->d_v3tab.as<int>();
+  const int* tile_col0 = h->d_v3tab.as<int>() + v.NP + 2 * v.c.CW;
+  const int nrt = (p.N1 + v.r.T - 1) / v.r.T;
+  const int rows_slots = h->num_sms * v.r.ctas_per_sm, cols_slots = h->num_sms * v.c.ctas_per_sm;
+  StageTimer timer(h, kStageCorrCols, 0);
+  if (two_lanes) {
+    CU(cudaEventRecord(h->ev_fork, h->stream));
+    for (int l = 0; l < h->nlanes; ++l) CU(cudaStreamWaitEvent(h->lane[l], h->ev_fork, 0));
+  }
+  int k = 0, nl = 0;
+  for (int dd0 = 0; dd0 < dc; dd0 += G)
+    for (int r0 = 0; r0 < R; r0 += Rc, ++k) {
+      ChunkV3 ck{r0, std::min(Rc, R - r0), dd0, std::min(G, dc - dd0)};
+      const int l = two_lanes ? k % h->nlanes : gnssacq::kMaxLanes;
+      cudaStream_t st = two_lanes ? h->lane[l] : h->stream;
+      float2* scr = two_lanes ? h->d_scratch_lane[l].as<float2>() : h->d_scratch.as<float2>();
+      const int pairs = ck.G * B;
+      int split = 1;                                  // split the (Doppler, block) list when the grid would not fill the GPU twice
+      if (nrt * ck.Rc < 2 * rows_slots) split = std::min(pairs, (2 * rows_slots + nrt * ck.Rc - 1) / (nrt * ck.Rc));
+      GNSSACQ_LAUNCH(v.r.fn, dim3(nrt, ck.Rc, split), dim3(v.r.threads), v.r.smem, st, p, h->d_X.as<float2>(), h->d_C.as<float2>(), ck, B, scr);
+      const int ntasks = ck.Rc * ck.G * v.ntiles;
+      GNSSACQ_LAUNCH(v.c.fn, dim3(std::min(ntasks, cols_slots)), dim3(v.c.threads), v.c.smem, st, pv, h->v3_map[l].map, v.F2, tile_col0,
+                     ck, B, D, d0, n_lags, scale, v.ntiles, h->d_parts.as<Part>(), d_qdump);
+      nl += 2;
+    }
+  h->launches += nl;
+  h->prof_launches[kStageCorrCols] += h->profiling ? nl : 0;
+  if (two_lanes)
+    for (int l = 0; l < h->nlanes; ++l) {
+      CU(cudaEventRecord(h->ev_join[l], h->lane[l]));
+      CU(cudaStreamWaitEvent(h->stream, h->ev_join[l], 0));
+    }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // Correlate one doppler chunk [d0, d0+dc) against all replicas.
 int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags, float scale, int ntiles, float* d_qdump) {
   return with_radix_class(h->hp.rclass, [&](auto rc) -> int {
@@ -397,7 +534,8 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (B > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
   const DevPlan& p = h->dp;
   const bool large = h->hp.large;
-  const int ntiles = large ? (p.N2 + kTileW - 1) / kTileW : 1;
+  const V3Setup v3 = large ? v3_setup(h, B > 1) : V3Setup();
+  const int ntiles = v3.on ? v3.ntiles : (large ? (p.N2 + kTileW - 1) / kTileW : 1);
   const float scale = 1.0f / (float)N;
   const size_t tbytes = (size_t)N * sizeof(float2);
 
@@ -409,7 +547,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   Dc = std::max(1, std::min(Dc, 65535 / B));
   if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
   int Uc = 0;
-  if (large) {
+  if (large && !v3.on) {
     // Units per launch: enough to keep the scratch L2-resident when that still fills the GPU,
     // but never fewer than two waves of columns-kernel CTAs (ntiles x units) — with many
     // non-coherent blocks one unit's scratch alone exceeds L2, and spilling it to HBM
@@ -435,7 +573,9 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   for (int d0 = 0; d0 < D; d0 += Dc) {
     const int dc = std::min(Dc, D - d0);
     if (int rc = forward<0>(h, nullptr, h->d_freq.as<double>() + d0, stride, B, dc * B, h->d_X.as<float2>())) return rc;
-    if (int rc = correlate_chunk(h, B, D, d0, dc, Uc, n_lags, scale, ntiles, d_qdump)) return rc;
+    if (v3.on) {
+      if (int rc = correlate_chunk_v3(h, v3, B, D, d0, dc, n_lags, scale, d_qdump)) return rc;
+    } else if (int rc = correlate_chunk(h, B, D, d0, dc, Uc, n_lags, scale, ntiles, d_qdump)) return rc;
   }
   {
     StageTimer timer(h, kStageFinalize, 1);
@@ -447,6 +587,45 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
 }
 
 }  // namespace
+
+namespace acq {
+#ifndef GNSSACQ_EMU_BUILD
+int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned long long dims[3],
+                             const unsigned long long strides_bytes[2], const unsigned box[3]) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static_assert(sizeof(CUtensorMap) == sizeof(TensorMap), "tensor map size");
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+  const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
+  const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), d, st, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+#else
+int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned long long dims[3],
+                             const unsigned long long strides_bytes[2], const unsigned box[3]) {
+  EmuTensorMap m{};
+  m.base = static_cast<const unsigned char*>(base);
+  m.rank = 3; m.esize = 8;
+  m.stride[0] = 8; m.stride[1] = (long long)strides_bytes[0]; m.stride[2] = (long long)strides_bytes[1];
+  for (int i = 0; i < 3; ++i) { m.dim[i] = (long long)dims[i]; m.box[i] = (int)box[i]; }
+  memset(out, 0, sizeof(*out));
+  memcpy(out, &m, sizeof(m));
+  return 0;
+}
+#endif
+}  // namespace acq
 
 // =============================================================================== C ABI
 extern "C" {
@@ -492,7 +671,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -653,6 +832,11 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
     h->use_gt = value != 0;
     return 0;
   }
+  if (std::string(name) == "v3") { h->use_v3 = value != 0; return 0; }
+  if (std::string(name) == "v3_rows") { h->v3_rows_variant = value; return 0; }
+  if (std::string(name) == "v3_cols") { h->v3_cols_variant = value; return 0; }
+  if (std::string(name) == "v3_rc") { h->v3_rc = value; return 0; }
+  if (std::string(name) == "v3_g") { h->v3_g = value; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }
   if (std::string(name) == "small_ctas") { h->small_ctas = value; return 0; }
   if (std::string(name) == "units_per_chunk") { h->force_uc = value; return 0; }
@@ -816,7 +1000,7 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
   return (find_rows_kernel(h->dp.s2, h->hp.gt) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0) |
-         (h->hp.gt ? 32 : 0);
+         (h->hp.gt ? 32 : 0) | (v3_setup(h, false).on ? 64 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

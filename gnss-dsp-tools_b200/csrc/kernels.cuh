@@ -35,6 +35,13 @@ struct DevPlan {
   const int* col_lag;
 };
 
+// Units of one launch of the kernels_v3.cuh pair: replicas [r0, r0+Rc) x chunk-local Doppler bins
+// [dd0, dd0+G) (x B blocks); scratch slot of (replica r, bin dd, block b) below.
+struct ChunkV3 { int r0, Rc, dd0, G; };
+__host__ __device__ __forceinline__ int v3_slot(const ChunkV3& ck, int B, int r, int dd, int b) {
+  return ((r - ck.r0) * ck.G + (dd - ck.dd0)) * B + b;
+}
+
 // Per-(replica, doppler, tile) partial result of the correlate kernel.
 struct Part {
   unsigned long long key;   // (float bits of max q) << 32 | (0xffffffff - lag): max key = max q, ties -> lowest lag

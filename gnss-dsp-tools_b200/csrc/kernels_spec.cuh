@@ -207,14 +207,16 @@ __device__ __forceinline__ float sqrt_fast(float a) {
 // SPLIT: share a radix-31 butterfly between two warps (halves its live registers; needed at 256
 // threads x 3 CTAs per SM). With 128-thread CTAs the butterfly fits in one thread's 128 registers
 // and the duplicated loads / twiddle multiplies of the shared form go away.
-template <class S, bool MULTI, int THREADS = kThreads, bool SPLIT = true>
+// TW = tile width (columns side by side in the tile, a power of two <= 16).
+template <class S, bool MULTI, int THREADS = kThreads, bool SPLIT = true, int TW = kTW>
 __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, const DevPlan& pl, int ncols, int lag0,
                                                 int b, bool last, int n_lags, float scale, float* qd,
                                                 float& best, int& bestlag, float& sum) {
-  constexpr int WP = kTileW;
+  static_assert(!SPLIT || TW == kTW, "the warp-pair butterfly assumes 16-column tiles");
+  constexpr int WP = TW;
   const int N2 = pl.N2;
-  const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
-  constexpr int nb = THREADS / kTW;
+  const int tc = threadIdx.x & (TW - 1), tb = threadIdx.x / TW;
+  constexpr int nb = THREADS / TW;
   const bool dump = qd != nullptr;
   constexpr int R0 = S::radix(0), m0 = S::stride(0);
   // A butterfly output sits at tile position pos = i + q*m0; the lag it stands for is

@@ -1,0 +1,214 @@
+// Copy-engine-fed correlate kernels for coprime (Good-Thomas) plans whose two tile transforms are
+// two-stage prime-factor schedules: 163680 = 341 x 480 (31*11, 15*32), 61380 = 279 x 220 (31*9, 11*20).
+//
+// Why: ncu on the register-loading kernels (kernels_small.cuh) shows them latency-bound — issue
+// slots 34-40 % busy, 53 % of the rows kernel's stall samples waiting on global loads — not
+// bandwidth-bound (profiles/README.md, r03a). Here the tiles are moved by the copy engine
+// (cp.async.bulk / cp.async.bulk.tensor + mbarrier transaction counts) while the butterflies of the
+// previous tile run, so no warp ever waits on a global load with data in registers:
+//
+//   rows kernel  one CTA = (tile of T rows, replica r); it keeps its slice of the replica spectrum
+//                C[r] in registers and walks the (Doppler, block) pairs of the chunk: the spectra
+//                tiles X[d][b] stream through a shared-memory ring (1-D bulk copies, they are
+//                contiguous), stage A = multiply + radix-RA butterflies over the stride-RB digit
+//                (lanes along the contiguous digit), exchange through a padded tile, stage B =
+//                radix-RB butterflies over 16-byte accesses in place, and the finished tile leaves
+//                as ONE bulk store. No four-step twiddle (coprime split), no stage twiddles
+//                (coprime radices), one shared-memory exchange.
+//   cols kernel  persistent CTAs; tile = N1 x CW scratch columns fetched with one 3-D tensor-map
+//                copy into a two-slot ring; first stage in place, then the radix-31 stage fused with
+//                |.|, the non-coherent sum and the peak search (cols_last_stage).
+//
+// Scratch layout (private to this pair): row p1 of slot s holds RA groups of PB = RB + pad
+// elements, element (a', b') at ((s*N1 + p1)*RA + a')*PB + b'; pad elements are never read as data
+// (col_lag_p marks them -1). The pad makes stage B's 16-byte accesses conflict-free and lets the
+// bulk store copy the tile verbatim.
+#pragma once
+#include "async_copy.cuh"
+#include "kernels_small.cuh"
+
+namespace acq {
+
+// pitch (elements) of one RB-group in the exchange tile: a multiple of 2 (16-byte accesses) with
+// pitch/2 odd, so 8 consecutive groups start in 8 different 16-byte bank groups
+__host__ __device__ constexpr int v3_pitch(int RB) {
+  int p = RB + (RB & 1);
+  while ((p / 2) % 2 == 0) p += 2;
+  return p;
+}
+
+// =========================================================================== rows kernel
+template <class S, int T, int XBUFS> __host__ __device__ constexpr size_t rows_v3_smem() {
+  return (size_t)XBUFS * T * S::F * sizeof(float2) + 2 * (size_t)T * S::radix(0) * v3_pitch(S::radix(1)) * sizeof(float2) + XBUFS * 8;
+}
+
+// grid = (row tiles, Rc, splits of the pair list); THREADS >= T * RB. X: [Dc][B][N], C: [R][N] (position order), scratch as above.
+template <class S, int T, int THREADS, int MINCTAS, int XBUFS>
+__global__ void __launch_bounds__(THREADS, MINCTAS)
+k_corr_rows_v3(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C, ChunkV3 ck, int B,
+               float2* __restrict__ scratch) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2 && S::kPfa, "two coprime stages");
+  constexpr int N2 = S::F, RA = S::radix(0), RB = S::radix(1), PB = v3_pitch(RB), NP = RA * PB;
+  static_assert(RB % 2 == 0 && THREADS >= T * RB && THREADS >= T * RA, "thread mapping");
+  constexpr int XT = T * N2, ET = T * NP;                     // float2 per X buffer / exchange buffer
+  float2* xbuf = smem;
+  float2* ebuf = smem + XBUFS * XT;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ebuf + 2 * ET);
+  const int N = pl.N, N1 = pl.N1;
+  const int row0 = blockIdx.x * T;
+  const int nrows = imin(T, N1 - row0);
+  const int r = ck.r0 + blockIdx.y;
+  // (Doppler, block) pairs, block fastest; grid.z splits the list so that short chunks still fill the GPU
+  const int nall = ck.G * B, per = (nall + gridDim.z - 1) / gridDim.z;
+  const int it0 = blockIdx.z * per, nit = imin(per, nall - it0);
+  const int tid = threadIdx.x;
+  const unsigned xbytes = (unsigned)nrows * N2 * sizeof(float2), ebytes = (unsigned)nrows * NP * sizeof(float2);
+
+  auto issue = [&](int it) {                                   // thread 0: spectra tile of pair `it` -> ring slot it % XBUFS
+    const int xs = it % XBUFS;
+    const int g = it0 + it;
+    const float2* src = X + ((long long)(ck.dd0 + g / B) * B + g % B) * N + (long long)row0 * N2;
+    mbar_arrive_expect(&full[xs], xbytes);
+    bulk_g2s(xbuf + xs * XT, src, xbytes, &full[xs]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < XBUFS; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    for (int it = 0; it < XBUFS && it < nit; ++it) issue(it);
+  }
+  // stage-A butterfly of this thread: row ra, contiguous digit b; its replica-spectrum values stay in registers
+  const int ra = tid / RB, b = tid - ra * RB;
+  const bool act_a = tid < T * RB && ra < nrows;
+  float2 c[RA];
+  if (act_a) {
+    const float2* cp = C + (long long)r * N + (long long)(row0 + ra) * N2 + b;
+#pragma unroll
+    for (int a = 0; a < RA; ++a) c[a] = __ldg(&cp[a * RB]);
+  }
+  const bool act_b = tid < nrows * RA;                         // stage-B butterfly: group tid = row * RA + a'
+  __syncthreads();                                             // barrier initialisation visible to every thread
+
+  for (int it = 0; it < nit; ++it) {
+    const int xs = it % XBUFS, e = it & 1;
+    float2* et = ebuf + e * ET;
+    mbar_wait(&full[xs], (unsigned)(it / XBUFS) & 1u);
+    if (act_a) {
+      const float2* xp = xbuf + xs * XT + ra * N2 + b;
+      float2 y[RA];
+#pragma unroll
+      for (int a = 0; a < RA; ++a) y[a] = cmulc(c[a], xp[a * RB]);
+      inv_dft<RA>(y);
+      float2* ep = et + ra * NP + b;
+#pragma unroll
+      for (int a = 0; a < RA; ++a) ep[a * PB] = y[a];
+    }
+    __syncthreads();                                           // exchange tile complete; ring slot xs drained
+    if (tid == 0 && it + XBUFS < nit) { fence_async_smem(); issue(it + XBUFS); }
+    if (act_b) {
+      float4* p4 = reinterpret_cast<float4*>(et + tid * PB);
+      float2 v[RB];
+#pragma unroll
+      for (int q = 0; q < RB / 2; ++q) { const float4 t = p4[q]; v[2 * q] = make_float2(t.x, t.y); v[2 * q + 1] = make_float2(t.z, t.w); }
+      inv_dft<RB>(v);
+#pragma unroll
+      for (int q = 0; q < RB / 2; ++q) p4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+      fence_async_smem();                                      // these writes are read by the bulk store below
+    }
+    if (tid == 0) bulk_wait_read<0>();                         // the store of pair it-1 has drained the other exchange buffer
+    __syncthreads();
+    if (tid == 0) {
+      const int g = it0 + it;
+      const int slot = v3_slot(ck, B, r, ck.dd0 + g / B, g % B);
+      bulk_s2g(scratch + ((long long)slot * N1 + row0) * NP, et, ebytes);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();                            // shared memory must outlive the last store
+}
+
+// =========================================================================== cols kernel
+// ring slots start on 128-byte boundaries (tensor-map copies need it)
+template <class S, int CW> __host__ __device__ constexpr int cols_v3_slot() { return (S::F * CW + 15) / 16 * 16; }   // float2 per slot
+template <class S, bool MULTI, int CW> __host__ __device__ constexpr size_t cols_v3_smem() {
+  return (size_t)2 * cols_v3_slot<S, CW>() * sizeof(float2) + (MULTI ? (size_t)S::F * CW * sizeof(float) : 0) + 16;
+}
+
+// Persistent: task t = blockIdx.x + k * gridDim.x = (unit ul of the chunk, column tile ct), B items each.
+// map: 8-byte elements, dims (NP, F1, F2 * slots), box (CW, F1, F2) with N1 = F1 * F2; zmul = F2.
+// pl.col_lag must point at the padded column table (NP + slack entries, -1 = pad column).
+template <class S, bool MULTI, int CW, int THREADS, int MINCTAS>
+__global__ void __launch_bounds__(THREADS, MINCTAS)
+k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, const int* __restrict__ tile_col0,
+               ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
+               Part* __restrict__ parts, float* __restrict__ q_dump) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2, "two-stage columns schedule");
+  static_assert(CW == 8 || CW == 16, "tile width");
+  constexpr int N1 = S::F, TILE = N1 * CW, SLOT = cols_v3_slot<S, CW>();
+  float* qs = reinterpret_cast<float*>(smem + 2 * SLOT);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v3_smem<S, MULTI, CW>() - 16);
+  const int N = pl.N;
+  const int tid = threadIdx.x, tc = tid & (CW - 1), tb = tid / CW;
+  constexpr int nb = THREADS / CW;
+  const int ntasks = ck.Rc * ck.G * ntiles;
+
+  auto issue = [&](int task, int b, int slot) {                // thread 0
+    const int ul = task / ntiles, ct = task - ul * ntiles;
+    mbar_arrive_expect(&full[slot], (unsigned)(TILE * sizeof(float2)));
+    tma_load_3d(smem + slot * SLOT, &map, __ldg(&tile_col0[ct]), 0, (ul * B + b) * zmul, &full[slot]);
+  };
+  int task = blockIdx.x, b = 0;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+    tma_prefetch_map(&map);
+    if (task < ntasks) issue(task, 0, 0);
+  }
+  __syncthreads();
+  float best = -1.f, sum = 0.f;
+  int bestlag = 0x7fffffff;
+  for (unsigned seq = 0; task < ntasks; ++seq) {
+    int ntask = task, nblk = b + 1;
+    if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
+    __syncthreads();                                           // every thread is done with the previous item: its slot is free
+    if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk, (seq + 1) & 1); }
+    const int ul = task / ntiles, ct = task - ul * ntiles;
+    const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
+    const int lag0 = __ldg(&tile_col0[ct]) + tc;
+    const int ncols = __ldg(&pl.col_lag[lag0]) >= 0 ? CW : 0;   // pad columns take no part in the peak search
+    float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
+    const bool last = (b + 1 == B);
+    if (b == 0) { best = -1.f; sum = 0.f; bestlag = 0x7fffffff; }
+    float2* tile = smem + (seq & 1) * SLOT;
+    mbar_wait(&full[seq & 1], (seq >> 1) & 1u);
+    {                                                          // first inverse stage: unit stride, in place
+      constexpr int R = S::radix(1), nbf = N1 / R;
+#pragma unroll 1
+      for (int bf = tb; bf < nbf; bf += nb) {
+        float2* p = tile + bf * R * CW + tc;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = p[q * CW];
+        inv_dft<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) p[q * CW] = v[q];
+      }
+    }
+    __syncthreads();
+    cols_last_stage<S, MULTI, THREADS, false, CW>(tile, qs, pl, ncols, lag0, b, last, n_lags, scale, qd, best, bestlag, sum);
+    if (last) {
+      unsigned long long key = bestlag != 0x7fffffff ? pack_key(best * scale, bestlag) : 0ull;
+      float s = sum * scale;
+      block_reduce_part(key, s);
+      if (tid == 0) {
+        Part p; p.key = key; p.sum = s; p.pad = 0.f;
+        parts[((long long)r * D + d0 + dd) * ntiles + ct] = p;
+      }
+    }
+    task = ntask; b = nblk;
+  }
+}
+
+}  // namespace acq

@@ -4,6 +4,7 @@
 #pragma once
 #include "fft_core.cuh"
 #include "kernels.cuh"
+#include "async_copy.cuh"
 
 namespace acq {
 
@@ -25,5 +26,15 @@ struct ColsSmall { corr_cols_fn fn; int threads; };
 constexpr int kRowsSmallTile = 8;
 RowsSmall find_rows_small(const SubPlan& s2, bool gt = false);
 ColsSmall find_cols_small(const SubPlan& s1, bool multi);
+
+// Copy-engine-fed pair for coprime plans with two-stage schedules (kernels_v3.cuh). `variant`
+// picks among the instantiated tile shapes (0 = default, measured fastest; A/B through the
+// "v3_rows" / "v3_cols" options); fn == nullptr when the schedule has none.
+typedef void (*rows_v3_fn)(DevPlan, const float2*, const float2*, ChunkV3, int, float2*);
+typedef void (*cols_v3_fn)(DevPlan, const TensorMap, int, const int*, ChunkV3, int, int, int, int, float, int, Part*, float*);
+struct RowsV3 { rows_v3_fn fn; int threads, T, ctas_per_sm; size_t smem; int RA, RB, PB; };
+struct ColsV3 { cols_v3_fn fn; int threads, CW, ctas_per_sm; size_t smem; };
+RowsV3 find_rows_v3(const SubPlan& s2, int variant);
+ColsV3 find_cols_v3(const SubPlan& s1, bool multi, int variant);
 
 }  // namespace acq

@@ -96,3 +96,40 @@ void emu_run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()
   emu_warps = nullptr;
   emu_dyn_smem = nullptr;
 }
+
+// ---------------------------------------------------------------- mbarrier stand-in (async_copy.cuh)
+// One record per barrier address: pending arrivals, expected transaction bytes and the phase
+// bit. A phase completes when both reach zero, as on the device.
+#include <unordered_map>
+namespace acq {
+namespace {
+struct MbarState { int init = 0, pending = 0; long long tx = 0; unsigned phase = 0; };
+std::mutex mbar_mu;
+std::unordered_map<const void*, MbarState> mbar_tab;
+void mbar_settle(MbarState& s) {
+  if (s.pending == 0 && s.tx == 0) { s.phase ^= 1u; s.pending = s.init; }
+}
+}  // namespace
+void emu_mbar_init(unsigned long long* bar, int count) {
+  std::lock_guard<std::mutex> g(mbar_mu);
+  MbarState s; s.init = s.pending = count;
+  mbar_tab[bar] = s;
+}
+void emu_mbar_arrive(unsigned long long* bar, long long tx) {
+  std::lock_guard<std::mutex> g(mbar_mu);
+  MbarState& s = mbar_tab.at(bar);
+  s.tx += tx;
+  s.pending -= 1;
+  mbar_settle(s);
+}
+void emu_mbar_complete_tx(unsigned long long* bar, long long bytes) {
+  std::lock_guard<std::mutex> g(mbar_mu);
+  MbarState& s = mbar_tab.at(bar);
+  s.tx -= bytes;
+  mbar_settle(s);
+}
+bool emu_mbar_test(unsigned long long* bar, unsigned parity) {
+  std::lock_guard<std::mutex> g(mbar_mu);
+  return mbar_tab.at(bar).phase != (parity & 1u);
+}
+}  // namespace acq

@@ -180,7 +180,48 @@ def test_large_163680_coprime_split_341x480(eng):
     """BASELINE config 2's transform as a coprime (Good-Thomas) four-step: 163680 = 341 x 480, no
     twiddle pass; 341 = 31*11 and 480 = 15*32 are themselves twiddle-free two-stage schedules."""
     info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
-    assert info['N1'] == 341 and info['N2'] == 480 and eng.kernel_variant() == 59
+    assert info['N1'] == 341 and info['N2'] == 480 and eng.kernel_variant() == 123      # 64: copy-engine-fed pair
+
+
+@pytest.mark.slow
+def test_large_163680_register_loading_kernels_on_the_coprime_split(eng):
+    """v3 = 0: the same plan through the register-loading kernels (kernels_small.cuh)."""
+    eng.set_option('v3', 0)
+    try:
+        info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
+        assert info['N1'] == 341 and eng.kernel_variant() == 59
+    finally:
+        eng.set_option('v3', 1)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4)])
+def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
+    """Every instantiated tile shape of the copy-engine-fed pair, with chunk shapes that leave ragged
+    edges (3 replicas in chunks of rc, 5 Doppler bins in groups of g)."""
+    for k, v in (('v3_rows', rows), ('v3_cols', cols), ('v3_rc', rc), ('v3_g', g)):
+        eng.set_option(k, v)
+    try:
+        _case(eng, 163680, False, False, True, 1, (-500, 750, 250), 16.368e6, nprn=3, lag_limit=16368)
+        assert eng.kernel_variant() & 64
+    finally:
+        for k in ('v3_rows', 'v3_cols', 'v3_rc', 'v3_g'):
+            eng.set_option(k, 0)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2)])
+def test_v3_non_coherent_blocks_61380(eng, rows, cols, blocks):
+    """279 x 220 with several non-coherent blocks: the (Doppler, block) list walked by the rows
+    kernel (split over grid.z), q accumulated in shared memory by the columns kernel."""
+    eng.set_option('v3_rows', rows)
+    eng.set_option('v3_cols', cols)
+    try:
+        _case(eng, 30690, True, False, False, blocks, (-400, 400, 200), 30.69e6, nprn=2)
+        assert eng.kernel_variant() & 64
+    finally:
+        eng.set_option('v3_rows', 0)
+        eng.set_option('v3_cols', 0)
 
 
 @pytest.mark.slow
