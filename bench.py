@@ -127,6 +127,102 @@ def _cpu_task(t):
     return orc.search(x, ca.ca_code(prn), FS, N, grid, 1, normalize=True, mod_L=True, lag_limit=N_LAGS, periods=10)
 
 
+# Other BASELINE configs, pinned in the same JSON line (`configs`): (name, n, pad, R, D, B, normalize).
+# Random capture and +-1 replicas of the right shape, resident on the device; one search each.
+EXTRA_CONFIGS = [
+    ('config1 acquire-gps-l1 PRN 1, 1 ms: 1 x 20 x 4096', 4096, False, 1, 20, 1, True),
+    ('config3 native E1B+E1C 20.46 Msps: 72 x 360 x 163680 (2 x 81840)', 81840, True, 72, 360, 1, False),
+    ('config4 native L5I+L5Q 25 Msps: 64 x 70 x 50000 (2 x 25000), 20 blocks', 25000, True, 64, 70, 20, False),
+    ('config4 reference-style 30.69 Msps: 64 x 70 x 61380 (2 x 30690), 20 blocks', 30690, True, 64, 70, 20, False),
+]
+STRONG = ('config4 native L5I+L5Q 25 Msps: 64 x 70 x 50000 (2 x 25000), 20 blocks, Doppler-sharded', 25000, True, 64, 70, 20, False)
+
+
+def shape_inputs(n, pad, R, B, seed=0):
+    rng = np.random.default_rng(seed)
+    Nf = 2 * n if pad else n
+    nx = (B - 1) * n + Nf
+    x = (rng.normal(0, 8, nx) + 1j * rng.normal(0, 8, nx)).astype(np.complex64)
+    rep = np.where(rng.integers(0, 2, (R, Nf)) > 0, 1, -1).astype(np.int8)
+    if pad:
+        rep[:, n:] = 0
+    return x, rep, Nf
+
+
+def bench_shape(eng, torch, stream, dev, cfg, peak, reps=3):
+    """One extra config on this GPU: search with resident capture and replica spectra."""
+    name, n, pad, R_, D_, B_, norm = cfg
+    x, rep, Nf = shape_inputs(n, pad, R_, B_)
+    eng.set_signal(x)
+    eng.set_replicas(rep)
+    f = -np.arange(-(D_ // 2), D_ - D_ // 2) * 1e-5
+    rec = torch.zeros(4 * R_, dtype=torch.int32, device=dev)
+    eng.search_device(f, n, B_, norm, 0, rec.data_ptr())
+    torch.cuda.synchronize()
+    eng.stage_times(reset=True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        eng.search_device(f, n, B_, norm, 0, rec.data_ptr())
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    st = eng.stage_times(reset=True)
+    corr_ms = (st['corr'][0] + st['corr_rows'][0]) / reps
+    cells = R_ * D_ * Nf
+    return {'name': name, 'R': R_, 'D': D_, 'N': Nf, 'B': B_, 'ms': ms, 'cells_per_s': cells / ms * 1e3,
+            'cell_blocks_per_s': cells * B_ / ms * 1e3, 'plan': eng.plan_info(), 'kernel_variant': eng.kernel_variant(),
+            'correlate_ms': corr_ms, 'roofline_frac': (16.0 * cells * B_ / (corr_ms * 1e-3) / 1e9 / peak) if corr_ms > 0 else None,
+            'roofline_frac_whole_search': 16.0 * cells * B_ / (ms * 1e-3) / 1e9 / peak}
+
+
+def bench_strong(eng, torch, dist, stream, dev, rank, world, reps=3):
+    """Strong scaling of a FIXED grid (BASELINE config 4 split): rank k searches its contiguous
+    Doppler shard, one all-gather of the per-replica records, max over ranks; rank 0 also times the
+    whole grid alone for the efficiency figure."""
+    from gnsstools import distributed as gd
+    name, n, pad, R_, D_, B_, norm = STRONG
+    x, rep, Nf = shape_inputs(n, pad, R_, B_)
+    eng.set_signal(x)
+    eng.set_replicas(rep)
+    f = -np.arange(-(D_ // 2), D_ - D_ // 2) * 1e-5
+    lo, hi = gd.doppler_shard(D_, rank, world)
+    rec = torch.zeros(4 * R_, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(world * 4 * R_, dtype=torch.int32, device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sharded():
+        if hi > lo:
+            eng.search_device(np.ascontiguousarray(f[lo:hi]), n, B_, norm, 0, rec.data_ptr())
+        dist.all_gather_into_tensor(gathered, rec)
+
+    def alone():
+        if rank == 0:
+            eng.search_device(f, n, B_, norm, 0, rec.data_ptr())
+
+    ms_w = timed(sharded)
+    ms_1 = timed(alone)
+    cells = R_ * D_ * Nf
+    return {'config': name, 'n_gpus': world, 'bins_per_rank': [gd.doppler_shard(D_, k, world)[1] - gd.doppler_shard(D_, k, world)[0] for k in range(world)],
+            'ms_sharded': ms_w, 'ms_1gpu_same_run': ms_1, 'cells_per_s': cells / ms_w * 1e3, 'cell_blocks_per_s': cells * B_ / ms_w * 1e3,
+            'speedup': ms_1 / ms_w, 'efficiency': ms_1 / (world * ms_w),
+            'tail': 'per-rank forward FFTs of its own bins only; replica set-up outside the timed region; one 16-byte-per-replica all-gather (latency-bound) after the last kernel'}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port: the reference is pure Python
     and cannot travel to the GPU box) on all host cores, same metric/config."""
@@ -163,6 +259,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the other BASELINE configs and the strong-scaling block')
     ap.add_argument('--opt', action='append', default=[], help='engine option name=value (A/B measurements)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
@@ -285,6 +382,7 @@ def main():
         if b['dbin'] >= 0 and bins[b['dbin']] == fd and abs((10.0 * CODE_L * b['lag'] / N) % CODE_L - phase) < 0.2:
             found += 1
 
+    strong = bench_strong(eng, torch, dist, stream, dev, rank, world) if world > 1 and not args.no_extra else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,12 +432,20 @@ def main():
                                 '~40 B per cell-block through L2 (X, C, four-step twiddle, scratch out and back) '
                                 'against 16 B algorithmic (profiles/r02f_corr_ncu_summary.txt)'},
     }
+    if not args.no_extra:
+        line['configs'] = [bench_shape(eng, torch, stream, dev, cfg, peak) for cfg in EXTRA_CONFIGS]
+    if strong is not None:
+        line['strong'] = strong
     if not args.no_cpu_baseline:
         v, dt, info = cpu_baseline(x.astype(np.complex128), list(range(1, 33)), bins[:D_PER_GPU])
         line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': info['cores'], 'kind': 'port', 'sample': info['sample']}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if found != len(sats):
+        # what was just timed returned wrong peaks: the figure above is not a measurement of the search
+        sys.stderr.write('bench.py: only %d of %d planted satellites recovered\n' % (found, len(sats)))
+        sys.exit(3)
 
 
 if __name__ == '__main__':

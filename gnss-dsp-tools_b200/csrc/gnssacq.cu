@@ -93,6 +93,7 @@ struct gnssacq {
   int v3_rows_variant = 0, v3_cols_variant = 0;      // tile shapes (registry.cu), A/B
   int v3_rc = 0, v3_g = 0;                           // replicas x Doppler bins per launch (0 = automatic)
   DevBuf d_v3tab;                                    // padded column table + tile origins
+  DevBuf d_hint;                                     // per (replica, Doppler) unit: best value reported so far (peak-search floor)
   int v3tab_key[4] = {0, 0, 0, 0};                   // (N, RB, PB, CW) the table was built for
   int v3_ntiles = 0;
   struct LaneMap { TensorMap map; const void* base = nullptr; long long slots = 0; int NP = 0, CW = 0; } v3_map[kMaxLanes + 1];
@@ -317,11 +318,11 @@ struct V3Setup {
 };
 
 // The pair runs when the plan is a coprime split and both tile transforms have an instantiation.
-V3Setup v3_setup(const gnssacq* h, bool multi) {
+V3Setup v3_setup(const gnssacq* h, bool multi, bool dump) {
   V3Setup v;
   if (!h->use_v3 || !h->use_spec || !h->hp.large || !h->hp.gt || !h->hp.s1.pfa || !h->hp.s2.pfa) return v;
   v.r = find_rows_v3(h->dp.s2, h->v3_rows_variant);
-  v.c = find_cols_v3(h->dp.s1, multi, h->v3_cols_variant);
+  v.c = find_cols_v3(h->dp.s1, multi, dump, h->v3_cols_variant);
   if (!v.r.fn || !v.c.fn) return v;
   if (v.r.smem > h->smem_optin || v.c.smem > h->smem_optin) return v;
   v.NP = v.r.RA * v.r.PB;
@@ -371,7 +372,7 @@ int v3_map_for(gnssacq* h, const V3Setup& v, int which, const void* base, long l
 void v3_chunk_shape(const gnssacq* h, int B, int dc, int& Rc, int& G) {
   G = h->v3_g > 0 ? h->v3_g : std::max(1, 4 / B);
   G = std::max(1, std::min(G, dc));
-  Rc = h->v3_rc > 0 ? h->v3_rc : 8;
+  Rc = h->v3_rc > 0 ? h->v3_rc : 16;                 // measured on config 2 (tools/ab_v3.py): 16 x 4 units per launch
   Rc = std::max(1, std::min(Rc, h->R));
 }
 
@@ -419,7 +420,7 @@ int correlate_chunk_v3(gnssacq* h, const V3Setup& v, int B, int D, int d0, int d
       GNSSACQ_LAUNCH(v.r.fn, dim3(nrt, ck.Rc, split), dim3(v.r.threads), v.r.smem, st, p, h->d_X.as<float2>(), h->d_C.as<float2>(), ck, B, scr);
       const int ntasks = ck.Rc * ck.G * v.ntiles;
       GNSSACQ_LAUNCH(v.c.fn, dim3(std::min(ntasks, cols_slots)), dim3(v.c.threads), v.c.smem, st, pv, h->v3_map[l].map, v.F2, tile_col0,
-                     ck, B, D, d0, n_lags, scale, v.ntiles, h->d_parts.as<Part>(), d_qdump);
+                     ck, B, D, d0, n_lags, scale, v.ntiles, h->d_parts.as<Part>(), d_qdump, h->d_hint.as<unsigned>());
       nl += 2;
     }
   h->launches += nl;
@@ -534,7 +535,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (B > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
   const DevPlan& p = h->dp;
   const bool large = h->hp.large;
-  const V3Setup v3 = large ? v3_setup(h, B > 1) : V3Setup();
+  const V3Setup v3 = large ? v3_setup(h, B > 1, d_qdump != nullptr) : V3Setup();
   const int ntiles = v3.on ? v3.ntiles : (large ? (p.N2 + kTileW - 1) / kTileW : 1);
   const float scale = 1.0f / (float)N;
   const size_t tbytes = (size_t)N * sizeof(float2);
@@ -542,6 +543,10 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (int rc = h->d_freq.ensure((size_t)D * sizeof(double))) return rc;
   CU(cudaMemcpyAsync(h->d_freq.p, nco_freq, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (int rc = h->d_parts.ensure((size_t)R * D * ntiles * sizeof(Part))) return rc;
+  if (v3.on) {
+    if (int rc = h->d_hint.ensure((size_t)R * D * sizeof(unsigned))) return rc;
+    CU(cudaMemsetAsync(h->d_hint.p, 0, (size_t)R * D * sizeof(unsigned), h->stream));
+  }
 
   int Dc = (int)std::max<size_t>(1, std::min<size_t>((size_t)D, h->xchunk_bytes / (tbytes * B)));
   Dc = std::max(1, std::min(Dc, 65535 / B));
@@ -671,7 +676,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -1000,7 +1005,7 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
   return (find_rows_kernel(h->dp.s2, h->hp.gt) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0) |
-         (h->hp.gt ? 32 : 0) | (v3_setup(h, false).on ? 64 : 0);
+         (h->hp.gt ? 32 : 0) | (v3_setup(h, false, false).on ? 64 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

@@ -54,13 +54,15 @@ constexpr int cols_load_unroll(int) { return GNSSACQ_COLS_LOAD_UNROLL; }      //
 constexpr int cols_load_unroll(int R) { return stage_unroll(R); }
 #endif
 
-// ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs
+// ---- inverse butterfly on registers: v[q] (already conj-twiddled) -> natural-order outputs.
+// IDFT(x)[k] = DFT(x)[-k mod R]: the forward butterfly followed by an index reversal, which is pure
+// register renaming in unrolled code. (The re/im swap form costs two MOVs per element once the
+// values live in the 64-bit register pairs the packed f32x2 instructions need: ncu counted 70
+// MOVs per radix-32 butterfly.)
 template <int R> __device__ __forceinline__ void inv_dft(float2* v) {
-#pragma unroll
-  for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
   Dft<R>::run(v);
 #pragma unroll
-  for (int q = 0; q < R; ++q) v[q] = cswap(v[q]);
+  for (int q = 1; q < (R + 1) / 2; ++q) { const float2 t = v[q]; v[q] = v[R - q]; v[R - q] = t; }
 }
 
 // ---- one in-shared-memory inverse stage (stage J of S). Element e of column c lives at
@@ -194,7 +196,10 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
 __device__ __forceinline__ float sqrt_fast(float a) {
 #if defined(__CUDA_ARCH__)
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));     // MUFU.SQRT, <= 1 ulp: far inside the 1e-4 budget
+  // one MUFU.SQRT, <= 1 ulp: far inside the 1e-4 budget. ftz: without it ptxas wraps the MUFU in a
+  // denormal rescue (FSETP + 2 FMUL per output, ncu: 93 extra FMULs per radix-31 butterfly); inputs are
+  // |v|^2 of correlation sums, never subnormal unless the capture is all zeros (then 0 either way).
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 #else
   return sqrtf(a);

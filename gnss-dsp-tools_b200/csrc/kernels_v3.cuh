@@ -134,14 +134,108 @@ template <class S, bool MULTI, int CW> __host__ __device__ constexpr size_t cols
   return (size_t)2 * cols_v3_slot<S, CW>() * sizeof(float2) + (MULTI ? (size_t)S::F * CW * sizeof(float) : 0) + 16;
 }
 
+// Last inverse stage (odd prime radix R0 at stride m0, one thread per butterfly) fused with |.|, the
+// non-coherent sum and the peak search. Written for the issue-slot budget ncu showed (profiles/
+// README.md, r03b): no re/im swaps (inverse output k is re + i*im of the symmetric sums, output
+// R0-k is re - i*im), no per-thread column mask in the hot path, dump and block accumulation as
+// template flags, and a peak search whose common path is one max and one compare per batch of
+// outputs: a candidate is looked at only if it reaches `floor_` = the best eligible value this
+// thread, its warp or — through `unit_hint` — any finished tile of the same (replica, Doppler) unit
+// has seen. Any such value is a lower bound of the unit's maximum, so no candidate for the unit's
+// (maximum, lowest lag) is ever skipped; tiles that cannot hold it simply report nothing.
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS>
+__device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, const DevPlan& pl, int lagc, int b, bool last,
+                                            int n_lags, float scale, float* qd, float hint,
+                                            float& best, int& bestlag, float& sum) {
+  constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
+  static_assert(R0 % 2 == 1 && R0 >= 7, "prime radix fused with the epilogue");
+  const int tc = threadIdx.x & (CW - 1), tb = threadIdx.x / CW;
+  constexpr int nb = THREADS / CW;
+  const int N2 = pl.N2, Nfull = pl.N;
+  auto lag_of = [&](int n1i, int q) -> int {
+    int n1;
+    if constexpr (S::kPfa) { n1 = n1i + q * (S::F / R0); n1 = n1 >= S::F ? n1 - S::F : n1; }
+    else n1 = n1i + q * m0;
+    const int l = n1 * N2 + lagc;
+    return l >= Nfull ? l - Nfull : l;                          // wraps only for coprime splits
+  };
+  for (int i = tb; i < m0; i += nb) {
+    const float2* p = tile + i * CW + tc;
+    float* qp = qs + i * CW + tc;
+    float2 a[H + 1], bq[H + 1];
+    const float2 x0 = p[0];
+    float2 s0 = x0;
+    static_for<1, H + 1>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const float2 u = p[j * m0 * CW], w = p[(R0 - j) * m0 * CW];
+      a[j] = cadd(u, w);
+      bq[j] = csub(u, w);
+      s0 = cadd(s0, a[j]);
+    });
+    int n1i = i;
+    if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
+    float floor_ = fmaxf(best, hint);
+#if defined(__CUDA_ARCH__)
+    floor_ = fmaxf(floor_, __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(fmaxf(floor_, 0.f)))));
+#endif
+    // NB outputs v[t] with digit qof(t): magnitudes, accumulation over blocks, sum, peak candidates
+    auto sink = [&](auto NBc, auto qof, const float2* v) {
+      constexpr int NB = decltype(NBc)::value;
+      float acc[NB];
+#pragma unroll
+      for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(fmaf(v[t].x, v[t].x, v[t].y * v[t].y));
+      if constexpr (MULTI) {
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+          float* q1 = qp + qof(t) * m0 * CW;
+          if (b > 0) acc[t] += *q1;
+          if (!last) *q1 = acc[t];
+        }
+        if (!last) return;
+      }
+      float m = acc[0];
+#pragma unroll
+      for (int t = 0; t < NB; ++t) sum += acc[t];
+#pragma unroll
+      for (int t = 1; t < NB; ++t) m = fmaxf(m, acc[t]);
+      if (m >= floor_) {
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+          if (acc[t] >= floor_) {
+            const int lag = lag_of(n1i, qof(t));
+            if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; floor_ = fmaxf(floor_, best); }
+          }
+        }
+      }
+      if constexpr (DUMP) {
+#pragma unroll
+        for (int t = 0; t < NB; ++t) qd[lag_of(n1i, qof(t))] = acc[t] * scale;
+      }
+    };
+    sink(std::integral_constant<int, 1>{}, [](int) { return 0; }, &s0);
+    prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
+      constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
+      float2 v[2 * nk];
+#pragma unroll
+      for (int t = 0; t < nk; ++t) {
+        v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
+        v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
+      }
+      sink(std::integral_constant<int, 2 * nk>{}, [](int t) { return (t & 1) ? R0 - (k0 + t / 2) : k0 + t / 2; }, v);
+    });
+  }
+}
+
 // Persistent: task t = blockIdx.x + k * gridDim.x = (unit ul of the chunk, column tile ct), B items each.
 // map: 8-byte elements, dims (NP, F1, F2 * slots), box (CW, F1, F2) with N1 = F1 * F2; zmul = F2.
 // pl.col_lag must point at the padded column table (NP + slack entries, -1 = pad column).
-template <class S, bool MULTI, int CW, int THREADS, int MINCTAS>
+// unit_hint[r*D + d]: float bits of the best eligible value any finished tile of that unit has
+// reported (zeroed by the host before the search); read at the start of a task, raised at its end.
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, const int* __restrict__ tile_col0,
                ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
-               Part* __restrict__ parts, float* __restrict__ q_dump) {
+               Part* __restrict__ parts, float* __restrict__ q_dump, unsigned* __restrict__ unit_hint) {
   GNSSACQ_DYN_SMEM(float2, smem);
   static_assert(S::NS == 2, "two-stage columns schedule");
   static_assert(CW == 8 || CW == 16, "tile width");
@@ -167,8 +261,8 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     if (task < ntasks) issue(task, 0, 0);
   }
   __syncthreads();
-  float best = -1.f, sum = 0.f;
-  int bestlag = 0x7fffffff;
+  float best = -1.f, sum = 0.f, hint = 0.f;
+  int bestlag = 0x7fffffff, lagc = -1;
   for (unsigned seq = 0; task < ntasks; ++seq) {
     int ntask = task, nblk = b + 1;
     if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
@@ -176,11 +270,14 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk, (seq + 1) & 1); }
     const int ul = task / ntiles, ct = task - ul * ntiles;
     const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
-    const int lag0 = __ldg(&tile_col0[ct]) + tc;
-    const int ncols = __ldg(&pl.col_lag[lag0]) >= 0 ? CW : 0;   // pad columns take no part in the peak search
-    float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
+    const long long unit = (long long)r * D + d0 + dd;
     const bool last = (b + 1 == B);
-    if (b == 0) { best = -1.f; sum = 0.f; bestlag = 0x7fffffff; }
+    if (b == 0) {
+      best = -1.f; sum = 0.f; bestlag = 0x7fffffff;
+      lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[ct]) + tc]);     // -1: pad column, takes no part in the epilogue
+      hint = __uint_as_float(__ldcg(&unit_hint[unit]));         // unscaled, exactly a value some tile has seen (may be stale: any lower bound will do)
+    }
+    float* qd = DUMP ? q_dump + unit * N : nullptr;
     float2* tile = smem + (seq & 1) * SLOT;
     mbar_wait(&full[seq & 1], (seq >> 1) & 1u);
     {                                                          // first inverse stage: unit stride, in place
@@ -197,14 +294,21 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
       }
     }
     __syncthreads();
-    cols_last_stage<S, MULTI, THREADS, false, CW>(tile, qs, pl, ncols, lag0, b, last, n_lags, scale, qd, best, bestlag, sum);
+    if (lagc >= 0) cols_v3_last<S, MULTI, DUMP, CW, THREADS>(tile, qs, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
     if (last) {
-      unsigned long long key = bestlag != 0x7fffffff ? pack_key(best * scale, bestlag) : 0ull;
+      // reduce on the unscaled value (the hint must be bit-exactly a value that occurred); the scaling
+      // by 1/N is monotonic, so the order and the ties of the keys are those of the scaled values
+      unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
       float s = sum * scale;
       block_reduce_part(key, s);
       if (tid == 0) {
-        Part p; p.key = key; p.sum = s; p.pad = 0.f;
-        parts[((long long)r * D + d0 + dd) * ntiles + ct] = p;
+        Part p; p.key = 0ull; p.sum = s; p.pad = 0.f;
+        if (key != 0ull) {
+          const unsigned vb = (unsigned)(key >> 32);
+          p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
+          atomicMax(&unit_hint[unit], vb);
+        }
+        parts[unit * ntiles + ct] = p;
       }
     }
     task = ntask; b = nblk;

@@ -105,21 +105,23 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
 #define TRY(S, V, T, TH, C, XB)                                                                                   \
   if (variant == V && schedule_matches<S>(s2))                                                                    \
     return RowsV3{k_corr_rows_v3<S, T, TH, C, XB>, TH, T, C, rows_v3_smem<S, T, XB>(), S::radix(0), S::radix(1), v3_pitch(S::radix(1))};
-  TRY(S480, 0, 4, 128, 3, 2) TRY(S480, 1, 8, 256, 1, 2) TRY(S480, 2, 8, 256, 2, 1) TRY(S480, 3, 4, 128, 4, 1)
+  TRY(S480, 0, 4, 128, 4, 1) TRY(S480, 1, 8, 256, 1, 2) TRY(S480, 2, 8, 256, 2, 1) TRY(S480, 3, 4, 128, 3, 2)
   TRY(S220, 0, 8, 160, 3, 2) TRY(S220, 1, 8, 160, 4, 1)
 #undef TRY
   return RowsV3{nullptr, 0, 0, 0, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 9
 // cols: (tile columns, threads, CTAs per SM)
-ColsV3 find_cols_v3(const SubPlan& s1, bool multi, int variant) {
+ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
+#define PICK(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v3_smem<S, M, CW>()}
 #define TRY(S, V, CW, TH, C)                                                                                      \
   if (variant == V && schedule_matches<S>(s1))                                                                    \
-    return multi ? ColsV3{k_corr_cols_v3<S, true, CW, TH, C>, TH, CW, C, cols_v3_smem<S, true, CW>()}             \
-                 : ColsV3{k_corr_cols_v3<S, false, CW, TH, C>, TH, CW, C, cols_v3_smem<S, false, CW>()};
-  TRY(S341, 0, 16, 192, 2) TRY(S341, 1, 8, 96, 5) TRY(S341, 2, 16, 256, 2)
-  TRY(S279, 0, 16, 160, 3) TRY(S279, 1, 8, 96, 5)
+    return multi ? (dump ? PICK(S, CW, TH, C, true, true) : PICK(S, CW, TH, C, true, false))                      \
+                 : (dump ? PICK(S, CW, TH, C, false, true) : PICK(S, CW, TH, C, false, false));
+  TRY(S341, 0, 8, 96, 5) TRY(S341, 1, 16, 192, 2) TRY(S341, 2, 16, 256, 2)
+  TRY(S279, 0, 8, 96, 5) TRY(S279, 1, 16, 160, 3)
 #undef TRY
+#undef PICK
   return ColsV3{nullptr, 0, 0, 0, 0};
 }
 #else

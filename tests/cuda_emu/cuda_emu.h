@@ -69,6 +69,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { retu
 template <class T> static inline T __shfl_sync(unsigned, T v, int s) { return emu_shfl(v, s); }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline long long __double2ll_rd(double a) { return (long long)std::floor(a); }

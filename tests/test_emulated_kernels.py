@@ -210,7 +210,7 @@ def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2)])
+@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2)])   # 279 x 220: two tile shapes each
 def test_v3_non_coherent_blocks_61380(eng, rows, cols, blocks):
     """279 x 220 with several non-coherent blocks: the (Doppler, block) list walked by the rows
     kernel (split over grid.z), q accumulated in shared memory by the columns kernel."""

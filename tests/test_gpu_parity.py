@@ -51,6 +51,8 @@ ENGINE_CASES = [
     ('D-l2cm-2x81920', 10230, 4096000.0, 81920, True, False, False, 1, (-40, 40, 20), 2, None),
     ('cfg2-163680-10ms', 1023, 16368000.0, 163680, False, False, True, 1, (-500, 500, 250), 3, 16368),
     ('cfg4-native-2x25000', 10230, 25000000.0, 25000, True, False, False, 4, (-400, 400, 200), 2, None),
+    # BASELINE config 3 at its native rate: Galileo E1 (4092 chips, BOC(1,1)), 4 ms at 20.46 Msps, zero-padded 2n = 163680
+    ('cfg3-native-2x81840-boc', 4092, 20460000.0, 81840, True, True, False, 1, (-100, 50, 50), 2, None),
     # 32736 = 186 x 176: prime-factor specialised columns transform (31*6) with a generic Cooley-Tukey rows transform (11*16)
     ('mixed-32736-2ms', 1023, 16368000.0, 32736, False, False, True, 2, (-500, 500, 250), 2, None),
 ]
@@ -125,6 +127,34 @@ def test_all_zero_and_short_inputs(eng):
         eng.search(np.array([0.0]), n, 3, True)     # needs 3 blocks, capture holds 2
     with pytest.raises(ValueError):
         eng.set_replicas(np.ones((1, 2 * 37), np.float32))
+
+
+@pytest.mark.parametrize('n', [4096, 16384, 61380, 163680])
+def test_device_tie_rules(eng, n):
+    """Exact ties on the device. A constant capture against an all-ones replica puts all the energy
+    in the DC bin, so every lag of every Doppler entry gets bit-identical q: numpy's argmax keeps
+    the first lag (acquire-gps-l1.py:34) and the strict '>' scan over Doppler bins keeps the first
+    bin (acquire-gps-l1.py:36-39). The same Doppler bin given three times and the same replica
+    given twice must therefore come back as (lag 0, bin 0), identically for both replicas —
+    every thread, tile and CTA of the peak search holds a tie and must resolve it downwards."""
+    x = np.full(2 * n, 3 + 4j, np.complex64)
+    rep = np.ones((2, n), np.float32)
+    eng.set_signal(x)
+    eng.set_replicas(rep)
+    f = np.zeros(3)
+    for normalize in (False, True):
+        m, l, d, q = eng.search(f, n, 2, normalize, dump=True)
+        assert list(l) == [0, 0] and list(d) == [0, 0], (n, normalize, l, d)
+        assert m[0] == m[1] and m[0] > 0
+        assert np.all(q == q[0, 0, 0])                       # the ties are exact, not approximate
+    # ties only among the allowed lags: the first of them
+    m, l, d = eng.search(f, n, 2, False, n_lags=n // 4)
+    assert list(l) == [0, 0] and list(d) == [0, 0]
+    # two different bins with equal metric is not constructible exactly; equal bins at positions (1, 2)
+    # behind a weaker bin 0 must return bin 1
+    f2 = np.array([0.25, 0.0, 0.0])                          # bin 0: quarter-cycle per sample -> no DC energy left
+    m, l, d = eng.search(f2, n, 2, False)
+    assert list(d) == [1, 1] and list(l) == [0, 0]
 
 
 def test_batch_invariance_and_determinism(eng):

@@ -61,13 +61,13 @@ for name, n, pad, R, D, B, norm in CASES:
     ref = run(name, n, pad, R, D, B, norm, base)
     nrows = 4 if N == 163680 else 2
     ncols = 3 if N == 163680 else 2
-    shapes = [(0, 0), (8, 4), (16, 2), (32, 1), (4, 8), (8, 2), (16, 4)] if B == 1 else [(0, 0), (2, 1), (4, 1), (8, 1), (16, 1)]
+    shapes = [(0, 0), (8, 4), (4, 8), (32, 4), (16, 8), (32, 2)] if B == 1 else [(0, 0), (8, 1), (16, 1), (32, 1)]
     # tile shapes at the default chunk shape
     for rv, cv in itertools.product(range(nrows), range(ncols)):
         got = run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rows=rv, v3_cols=cv))
         if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
             print('   !! lags differ from the register-loading kernels')
     # chunk shapes and lanes at the default tiles
-    for (rc, g), lanes in itertools.product(shapes, (1, 2, 3)):
+    for (rc, g), lanes in itertools.product(shapes, (2, 3)):
         run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rc=rc, v3_g=g, lanes=lanes))
 eng.close()
