@@ -213,6 +213,17 @@ inline std::vector<float2> unit_roots(HostSubPlan& sp) {
   return t;
 }
 
+// Whether make_plan accepts N (same conditions, no tables built).
+inline bool plannable(int N) {
+  if (N < 4) return false;
+  for (int p : prime_factors(N))
+    if (!radix_supported(p)) return false;
+  int best = 0;
+  for (int a = 1; (long long)a * a <= N; ++a)
+    if (N % a == 0 && N / a <= kMaxSub) best = a;
+  return best >= 2;
+}
+
 // Choose N = N1*N2 with both factors tile-sized and as square as possible.
 // use_pfa(plan, which): whether the kernels that will run sub-transform `which` (1: length N1,
 // 2: length N2) are the twiddle-free prime-factor ones (asked only for coprime schedules; the plan

@@ -79,10 +79,12 @@ struct gnssacq {
   CubeTw cube_tw{nullptr, nullptr};
   DevBuf d_C;                         // replica spectra [R][N]
   int R = 0, N = 0;
+  int embed_n = 0;                    // != 0: the caller's transform length, embedded in the planned length N (>= 2*embed_n - 1)
 
   DevBuf d_X, d_scratch, d_parts, d_freq, d_rec, d_q, d_tmp;
   DevBuf d_raw, d_ext, d_y1, d_z, d_fir, d_pre128;        // capture front end
   DevBuf d_chips, d_base, d_bank;                         // replica builder / correlator bank
+  DevBuf d_repext;                                        // periodically extended replicas of an embedded length
 
   // optional per-stage timing (gnssacq_set_profiling): event pairs recorded around the
   // launches of each stage, folded into prof_ms at gnssacq_get_stage_times().
@@ -121,6 +123,10 @@ struct gnssacq {
 
 namespace {
 
+// plan-specialised kernels: off for embedded lengths, whose zero-padded blocks and partial sums only
+// the generic kernels implement
+bool spec_on(const gnssacq* h) { return h->use_spec && h->embed_n == 0; }
+
 int upload_nco(gnssacq* h) {
   std::vector<float2> f32(kNcoSize);
   for (int k = 0; k < kNcoSize; ++k)
@@ -153,7 +159,7 @@ int upload_plan(gnssacq* h, int N) {
   // A coprime radix schedule runs as a twiddle-free prime-factor transform when every kernel that
   // touches that sub-transform is a plan-specialised one (they carry the index maps; the generic
   // runtime-planned kernels are Cooley-Tukey only).
-  const bool spec = h->use_spec;
+  const bool spec = spec_on(h);
   const std::function<bool(const HostPlan&, int)> use_pfa = [spec](const HostPlan& hpl, int which) {
     if (!spec) return false;
     auto schedule_of = [](const HostSubPlan& hs, bool pfa) {      // schedule only: the twiddle tables do not exist yet
@@ -219,6 +225,8 @@ int upload_plan(gnssacq* h, int N) {
   h->dp.pos2_of_n = h->d_maps.as<int>() + hp.N1 + hp.N2;
   h->dp.col_lag = h->d_maps.as<int>() + hp.N1 + 2 * hp.N2;
   h->dp.gt = hp.gt ? 1 : 0;
+  h->dp.xlen = h->embed_n ? h->embed_n : hp.N;
+  h->dp.sum_lags = h->dp.xlen;
   h->dp.fpos1 = h->d_maps.as<int>() + hp.N1 + 3 * hp.N2;
   h->dp.fpos2 = h->dp.fpos1 + hp.N1;
   h->hp = std::move(hp);
@@ -281,7 +289,7 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
     const DevPlan& p = h->dp;
     const float2* tab = h->d_nco_f32.as<float2>();
     StageTimer timer(h, kStageFwd, h->hp.large ? 2 : 1);
-    if (h->hp.cube && h->use_spec) {
+    if (h->hp.cube && spec_on(h)) {
       auto kern = k_fwd_cube<SRC>;
       GNSSACQ_LAUNCH(kern, dim3(nt), dim3(256), (size_t)kCubeSmem, h->stream, h->cube_tw, h->d_x, rep, d_freq, tab, stride, B, X);
       h->launches += 1;
@@ -293,8 +301,8 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
       h->launches += 1;
     } else {
       const size_t smc = cols_smem(p, false), smr = rows_smem(p);
-      fwd_cols_fn kc = h->use_spec ? find_fwd_cols_kernel(p.s1, SRC) : nullptr;
-      fwd_rows_fn kr = h->use_spec ? find_fwd_rows_kernel(p.s2) : nullptr;
+      fwd_cols_fn kc = spec_on(h) ? find_fwd_cols_kernel(p.s1, SRC) : nullptr;
+      fwd_rows_fn kr = spec_on(h) ? find_fwd_rows_kernel(p.s2) : nullptr;
       if (!kc) kc = k_fwd_cols<RC, SRC>;
       if (!kr) kr = k_fwd_rows<RC>;
       if (int rc2 = allow_smem(h, kc, smc)) return rc2;
@@ -320,7 +328,7 @@ struct V3Setup {
 // The pair runs when the plan is a coprime split and both tile transforms have an instantiation.
 V3Setup v3_setup(const gnssacq* h, bool multi, bool dump) {
   V3Setup v;
-  if (!h->use_v3 || !h->use_spec || !h->hp.large || !h->hp.gt || !h->hp.s1.pfa || !h->hp.s2.pfa) return v;
+  if (!h->use_v3 || !spec_on(h) || !h->hp.large || !h->hp.gt || !h->hp.s1.pfa || !h->hp.s2.pfa) return v;
   v.r = find_rows_v3(h->dp.s2, h->v3_rows_variant);
   v.c = find_cols_v3(h->dp.s1, multi, dump, h->v3_cols_variant);
   if (!v.r.fn || !v.c.fn) return v;
@@ -370,7 +378,7 @@ int v3_map_for(gnssacq* h, const V3Setup& v, int which, const void* base, long l
 
 // Chunk shape of the pair: replicas x Doppler bins per launch.
 void v3_chunk_shape(const gnssacq* h, int B, int dc, int& Rc, int& G) {
-  G = h->v3_g > 0 ? h->v3_g : std::max(1, 4 / B);
+  G = h->v3_g > 0 ? h->v3_g : std::max(1, 8 / B);    // measured on config 2 (tools/ab_v3.py): 16 x 8 units per launch
   G = std::max(1, std::min(G, dc));
   Rc = h->v3_rc > 0 ? h->v3_rc : 16;                 // measured on config 2 (tools/ab_v3.py): 16 x 4 units per launch
   Rc = std::max(1, std::min(Rc, h->R));
@@ -440,7 +448,7 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
     constexpr int RC = decltype(rc)::value;
     const DevPlan& p = h->dp;
     const int R = h->R;
-    if (h->hp.cube && h->use_spec) {
+    if (h->hp.cube && spec_on(h)) {
       StageTimer timer(h, kStageCorrCols, 1);
       if (B > 1)
         GNSSACQ_LAUNCH(k_corr_cube<true>, dim3(R * dc), dim3(256), (size_t)kCubeSmem, h->stream, h->cube_tw, h->d_X.as<float2>(),
@@ -461,14 +469,14 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
       size_t smr = rows_smem(p);
       const size_t smc = cols_smem(p, B > 1);
       const bool gt = p.gt != 0;
-      corr_rows_fn kr = h->use_spec ? find_rows_kernel(p.s2, gt) : nullptr;
-      corr_cols_fn kc = h->use_spec ? find_cols_kernel(p.s1, B > 1) : nullptr;
+      corr_rows_fn kr = spec_on(h) ? find_rows_kernel(p.s2, gt) : nullptr;
+      corr_cols_fn kc = spec_on(h) ? find_cols_kernel(p.s1, B > 1) : nullptr;
       int tr = kThreads, tcn = kThreads, row_tile = kTileW;
-      if (h->use_spec && (h->small_ctas & 1)) {
+      if (spec_on(h) && (h->small_ctas & 1)) {
         const RowsSmall rs = find_rows_small(p.s2, gt);
         if (rs.fn) { kr = rs.fn; tr = rs.threads; smr = rs.smem; row_tile = kRowsSmallTile; }
       }
-      if (h->use_spec && (h->small_ctas & 2)) {
+      if (spec_on(h) && (h->small_ctas & 2)) {
         const ColsSmall cs = find_cols_small(p.s1, B > 1);
         if (cs.fn) { kc = cs.fn; tcn = cs.threads; }
       }
@@ -523,15 +531,18 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
 }
 
 int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int normalize, int n_lags,
-               Record* d_out, float* d_qdump) {
+               Record* d_out, float* d_qdump, int group_len = 0) {
   if (!h->d_x) return fail(GNSSACQ_ESTATE, "gnssacq_set_signal has not been called");
   if (h->R <= 0) return fail(GNSSACQ_ESTATE, "gnssacq_set_replicas has not been called");
   if (!nco_freq || D <= 0 || B <= 0 || stride < 0) return fail(GNSSACQ_EINVAL, "bad search arguments");
   const int N = h->N, R = h->R;
-  if ((int64_t)(B - 1) * stride + N > h->n_x)
+  const int Nuser = h->embed_n ? h->embed_n : N;              // the caller's transform length (= number of lags)
+  if ((int64_t)(B - 1) * stride + Nuser > h->n_x)
     return fail(GNSSACQ_EINVAL, "capture too short: need (n_blocks-1)*block_stride + N = " +
-                                    std::to_string((int64_t)(B - 1) * stride + N) + " samples, have " + std::to_string(h->n_x));
-  if (n_lags <= 0 || n_lags > N) n_lags = N;
+                                    std::to_string((int64_t)(B - 1) * stride + Nuser) + " samples, have " + std::to_string(h->n_x));
+  if (n_lags <= 0 || n_lags > Nuser) n_lags = Nuser;
+  if (group_len <= 0) group_len = D;
+  if (D % group_len != 0 || D / group_len > 65535) return fail(GNSSACQ_EINVAL, "the Doppler list is not a whole number of groups");
   if (B > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
   const DevPlan& p = h->dp;
   const bool large = h->hp.large;
@@ -562,7 +573,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
     // The 128-thread columns kernel runs 4 CTAs per SM: size a launch to just under one full wave
     // of them — 95 %, so that the other lane's rows kernel finds free slots at once — not just over
     // (measured on config 2, profiles/r02_units_per_chunk_sweep.log: 20 units 2.94 ms, 21-64 units 3.03-3.12 ms).
-    const bool small_cols = h->use_spec && (h->small_ctas & 2) && find_cols_small(p.s1, B > 1).fn != nullptr;
+    const bool small_cols = spec_on(h) && (h->small_ctas & 2) && find_cols_small(p.s1, B > 1).fn != nullptr;
     const size_t fill = small_cols ? std::max<size_t>(1, (size_t)(4 * h->num_sms * 19 / 20) / ntiles)
                                    : (size_t)(4 * h->num_sms + ntiles - 1) / ntiles;
     size_t uc = std::max(budget / unit_bytes, fill);
@@ -584,7 +595,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   }
   {
     StageTimer timer(h, kStageFinalize, 1);
-    GNSSACQ_LAUNCH(k_finalize, dim3(R), dim3(128), 0, h->stream, h->d_parts.as<Part>(), D, ntiles, N, normalize, d_out);
+    GNSSACQ_LAUNCH(k_finalize, dim3(R, D / group_len), dim3(128), 0, h->stream, h->d_parts.as<Part>(), D, group_len, ntiles, Nuser, normalize, d_out);
   }
   h->launches += 1;
   CU(cudaGetLastError());
@@ -676,7 +687,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint, &h->d_repext})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -723,7 +734,32 @@ int gnssacq_set_signal_device(gnssacq_t* h, const void* dev_iq, int64_t n) {
 }
 
 static int replicas_from_device(gnssacq_t* h, const float* d_rep, int32_t R, int32_t N) {
+  // Lengths the planner cannot factor (a prime factor outside {2,3,5,7,11,13,31}, or no split into
+  // two factors <= 1024) run embedded in the next power of two M >= 2N-1: periodically extended
+  // replica, zero-padded capture blocks, lags 0..N-1 kept — the same circular correlation, at the
+  // price of a longer transform and the generic kernels.
+  {
+    int want = 0;
+    if (!plannable(N)) {
+      long long M = 1;
+      while (M < 2ll * N - 1) M <<= 1;
+      if (N < 4 || M > (long long)kMaxSub * kMaxSub)
+        return fail(GNSSACQ_EINVAL, "FFT length " + std::to_string(N) + " is neither plannable (prime factors 2, 3, 5, 7, 11, 13, 31, two factors <= 1024) "
+                                    "nor short enough to embed in a power-of-two transform (N <= 524288)");
+      want = N;
+      N = (int32_t)M;
+    }
+    if (want != h->embed_n) { h->embed_n = want; h->plan_dirty = true; }
+  }
   if (int rc = upload_plan(h, N)) return rc;
+  if (h->embed_n) {
+    if (int rc = h->d_repext.ensure((size_t)R * N * sizeof(float))) return rc;
+    GNSSACQ_LAUNCH(k_extend_replicas, dim3(std::min((N + kThreads - 1) / kThreads, 1024), R), dim3(kThreads), 0, h->stream, d_rep, h->embed_n, N,
+                   h->d_repext.as<float>());
+    h->launches += 1;
+    CU(cudaGetLastError());
+    d_rep = h->d_repext.as<float>();
+  }
   if (int rc = h->d_C.ensure((size_t)R * N * sizeof(float2))) return rc;
   h->R = 0; h->N = N;
   // grid.y of the large path is limited to 65535 transforms per launch
@@ -919,9 +955,31 @@ int gnssacq_search(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t bloc
   if (int rc = run_search(h, nco_freq, D, block_stride, n_blocks, normalize, n_lags, h->d_rec.as<Record>(), d_q)) return rc;
   std::vector<Record> rec(h->R);
   CU(cudaMemcpyAsync(rec.data(), h->d_rec.p, rec.size() * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
-  if (q_dump) CU(cudaMemcpyAsync(q_dump, d_q, qn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (q_dump) {
+    if (h->embed_n)            // the device grid has the planned length per row; the caller gets lags 0..N-1
+      CU(cudaMemcpy2DAsync(q_dump, (size_t)h->embed_n * sizeof(float), d_q, (size_t)h->N * sizeof(float), (size_t)h->embed_n * sizeof(float),
+                           (size_t)h->R * D, cudaMemcpyDeviceToHost, h->stream));
+    else
+      CU(cudaMemcpyAsync(q_dump, d_q, qn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < h->R; ++r) { metric[r] = rec[r].metric; lag[r] = rec[r].lag; dbin[r] = rec[r].dbin; }
+  return 0;
+}
+
+int gnssacq_search_grouped(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t group_len, int32_t block_stride,
+                           int32_t n_blocks, int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin) {
+  if (!h || !metric || !lag || !dbin) return fail(GNSSACQ_EINVAL, "NULL argument");
+  if (group_len <= 0 || D <= 0 || D % group_len != 0) return fail(GNSSACQ_EINVAL, "the Doppler list is not a whole number of groups");
+  CU(cudaSetDevice(h->device));
+  if (h->R <= 0) return fail(GNSSACQ_ESTATE, "gnssacq_set_replicas has not been called");
+  const size_t nrec = (size_t)h->R * (D / group_len);
+  if (int rc = h->d_rec.ensure(nrec * sizeof(Record))) return rc;
+  if (int rc = run_search(h, nco_freq, D, block_stride, n_blocks, normalize, n_lags, h->d_rec.as<Record>(), nullptr, group_len)) return rc;
+  std::vector<Record> rec(nrec);
+  CU(cudaMemcpyAsync(rec.data(), h->d_rec.p, nrec * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < nrec; ++i) { metric[i] = rec[i].metric; lag[i] = rec[i].lag; dbin[i] = rec[i].dbin; }
   return 0;
 }
 
@@ -1002,6 +1060,7 @@ int64_t gnssacq_launch_count(gnssacq_t* h) { return h ? h->launches : 0; }
 
 int gnssacq_kernel_variant(gnssacq_t* h) {
   if (!h || h->hp.N == 0) return fail(GNSSACQ_ESTATE, "no plan yet");
+  if (h->embed_n) return 128;                                   // embedded length: generic kernels on a power-of-two plan
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
   return (find_rows_kernel(h->dp.s2, h->hp.gt) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0) |

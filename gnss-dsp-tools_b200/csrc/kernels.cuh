@@ -33,6 +33,11 @@ struct DevPlan {
   const int* fpos1;
   const int* fpos2;
   const int* col_lag;
+  // Embedded lengths (gnssacq.cu, any N the planner cannot factor runs inside a longer power-of-two
+  // transform): capture samples at block offsets >= xlen read as zero and only lags < sum_lags enter
+  // the sum behind the mean. Both equal N otherwise; honoured by the generic kernels, which are the
+  // ones an embedded plan runs.
+  int xlen, sum_lags;
 };
 
 // Units of one launch of the kernels_v3.cuh pair: replicas [r0, r0+Rc) x chunk-local Doppler bins
@@ -138,7 +143,7 @@ k_fwd_mid(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ re
 
   for (int n1 = tb; n1 < N1; n1 += nb)
     for (int n2 = tc; n2 < N2; n2 += kTW)
-      A[n1 * SA + n2] = load_input<SRC>(x, rep, nco_tab, f, base, n1 * N2 + n2);
+      A[n1 * SA + n2] = (SRC == 0 && n1 * N2 + n2 >= pl.xlen) ? make_float2(0.f, 0.f) : load_input<SRC>(x, rep, nco_tab, f, base, n1 * N2 + n2);
   __syncthreads();
   subfft_tile<RC, false>(A, SA, N2, pl.s1);
   for (int p1 = tb; p1 < N1; p1 += nb)
@@ -192,7 +197,7 @@ k_corr_mid(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ 
         if (b > 0) acc += qs[lag];
         if (!last) { qs[lag] = acc; }
         else {
-          sum += acc;
+          if (lag < pl.sum_lags) sum += acc;
           if (lag < n_lags) { const unsigned long long k = pack_key(acc, lag); key = k > key ? k : key; }
           if (q_dump) q_dump[((long long)r * D + d0 + dd) * N + lag] = acc;
         }
@@ -233,7 +238,7 @@ k_fwd_cols(DevPlan pl, const float2* __restrict__ x, const float* __restrict__ r
     for (int n1 = tb; n1 < N1; n1 += nb) {
       const int n = n1 * N2 + col0 + tc;
       const int row = pl.gt ? __ldg(&pl.fpos1[n % N1]) : n1;
-      tile[row * kTileW + tc] = load_input<SRC>(x, rep, nco_tab, f, base, n);
+      tile[row * kTileW + tc] = (SRC == 0 && n >= pl.xlen) ? make_float2(0.f, 0.f) : load_input<SRC>(x, rep, nco_tab, f, base, n);
     }
   __syncthreads();
   subfft_tile<RC, false>(tile, kTileW, ncols, pl.s1);
@@ -328,7 +333,7 @@ k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D,
         if (b > 0) acc += qs[n1 * kTileW + tc];
         if (!last) { qs[n1 * kTileW + tc] = acc; }
         else {
-          sum += acc;
+          if (lag < pl.sum_lags) sum += acc;
           if (lag < n_lags) { const unsigned long long k = pack_key(acc, lag); key = k > key ? k : key; }
           if (q_dump) q_dump[((long long)r * D + d0 + dd) * N + lag] = acc;
         }
@@ -347,13 +352,16 @@ k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D,
 // doppler bin with the reference's rule — strict '>' scanning ascending bins from 0, so ties
 // go to the lowest bin and nothing is selected unless some metric is > 0
 // (acquire-gps-l1.py:25,36-39).
+// Doppler groups: the D entries of a call may be G consecutive groups of Dg (GLONASS FDMA: one
+// group per channel, acquire-glonass-l1.py:26-39); grid = (R, G), record g*R + r, dbin relative to
+// the group.
 static __global__ void __launch_bounds__(128)
-k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normalize, Record* __restrict__ out) {
-  const int r = blockIdx.x;
+k_finalize(const Part* __restrict__ parts, int D, int Dg, int ntiles, int N, int normalize, Record* __restrict__ out) {
+  const int r = blockIdx.x, g0 = blockIdx.y * Dg;
   unsigned long long best = 0ull;
   float dummy = 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const Part* p = parts + ((long long)r * D + d) * ntiles;
+  for (int d = threadIdx.x; d < Dg; d += blockDim.x) {
+    const Part* p = parts + ((long long)r * D + g0 + d) * ntiles;
     unsigned long long key = 0ull;
     float sum = 0.f;
     for (int t = 0; t < ntiles; ++t) { key = p[t].key > key ? p[t].key : key; sum += p[t].sum; }
@@ -369,14 +377,14 @@ k_finalize(const Part* __restrict__ parts, int D, int ntiles, int N, int normali
     Record rec; rec.metric = 0.f; rec.lag = 0; rec.dbin = -1; rec.pad = 0;
     if (best != 0ull) {
       const int d = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
-      const Part* p = parts + ((long long)r * D + d) * ntiles;
+      const Part* p = parts + ((long long)r * D + g0 + d) * ntiles;
       unsigned long long key = 0ull;
       for (int t = 0; t < ntiles; ++t) key = p[t].key > key ? p[t].key : key;
       rec.metric = __uint_as_float((unsigned)(best >> 32));
       rec.lag = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
       rec.dbin = d;
     }
-    out[r] = rec;
+    out[(long long)blockIdx.y * gridDim.x + r] = rec;
   }
 }
 
@@ -385,6 +393,16 @@ static __global__ void __launch_bounds__(kThreads)
 k_i8_to_f32(const signed char* __restrict__ in, long long n, float* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i];
+}
+
+// Periodic extension of a length-n replica into a length-M transform (M >= 2n-1): sample m < 2n-1
+// takes rep[m mod n], the rest is zero, so that the circular correlation of length M equals the
+// circular correlation of length n at lags 0..n-1 when the capture block is zero-padded.
+static __global__ void __launch_bounds__(kThreads)
+k_extend_replicas(const float* __restrict__ rep, int n, int M, float* __restrict__ out) {
+  const long long r = blockIdx.y;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x)
+    out[r * M + m] = m < 2 * n - 1 ? rep[r * n + (m >= n ? m - n : m)] : 0.f;
 }
 
 // ============================================================================ capture mix

@@ -174,10 +174,7 @@ __device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, cons
     });
     int n1i = i;
     if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
-    float floor_ = fmaxf(best, hint);
-#if defined(__CUDA_ARCH__)
-    floor_ = fmaxf(floor_, __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(fmaxf(floor_, 0.f)))));
-#endif
+    float floor_ = fmaxf(fmaxf(best, hint), 0.f);
     // NB outputs v[t] with digit qof(t): magnitudes, accumulation over blocks, sum, peak candidates
     auto sink = [&](auto NBc, auto qof, const float2* v) {
       constexpr int NB = decltype(NBc)::value;
@@ -199,13 +196,25 @@ __device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, cons
 #pragma unroll
       for (int t = 1; t < NB; ++t) m = fmaxf(m, acc[t]);
       if (m >= floor_) {
+        // rare once the floor is warm. The digit goes through an opaque move so that the lag arithmetic
+        // stays inside the branch (ptxas otherwise hoists ~100 integer instructions per butterfly into
+        // the common path).
 #pragma unroll
         for (int t = 0; t < NB; ++t) {
           if (acc[t] >= floor_) {
-            const int lag = lag_of(n1i, qof(t));
-            if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; floor_ = fmaxf(floor_, best); }
+            int q = qof(t);
+#if defined(__CUDA_ARCH__)
+            asm volatile("" : "+r"(q));
+#endif
+            const int lag = lag_of(n1i, q);
+            if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; }
           }
         }
+        floor_ = fmaxf(floor_, best);
+#if defined(__CUDA_ARCH__)
+        // share the new floor with the lanes that came along (a lower bound of the unit maximum)
+        floor_ = __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(floor_)));
+#endif
       }
       if constexpr (DUMP) {
 #pragma unroll
@@ -246,9 +255,11 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
   const int tid = threadIdx.x, tc = tid & (CW - 1), tb = tid / CW;
   constexpr int nb = THREADS / CW;
   const int ntasks = ck.Rc * ck.G * ntiles;
-
+  // Tasks are tile-major (task = ct * units + ul): the tiles of one unit are spread over the waves of
+  // the persistent grid, so all but the first carry a peak-search floor from the unit's earlier tiles.
+  const int nunits = ck.Rc * ck.G;
   auto issue = [&](int task, int b, int slot) {                // thread 0
-    const int ul = task / ntiles, ct = task - ul * ntiles;
+    const int ct = task / nunits, ul = task - ct * nunits;
     mbar_arrive_expect(&full[slot], (unsigned)(TILE * sizeof(float2)));
     tma_load_3d(smem + slot * SLOT, &map, __ldg(&tile_col0[ct]), 0, (ul * B + b) * zmul, &full[slot]);
   };
@@ -268,7 +279,7 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
     __syncthreads();                                           // every thread is done with the previous item: its slot is free
     if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk, (seq + 1) & 1); }
-    const int ul = task / ntiles, ct = task - ul * ntiles;
+    const int ct = task / nunits, ul = task - ct * nunits;
     const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
     const long long unit = (long long)r * D + d0 + dd;
     const bool last = (b + 1 == B);

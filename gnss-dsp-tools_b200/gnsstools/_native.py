@@ -44,6 +44,7 @@ def _declare(lib):
         'gnssacq_get_stage_times': [p, p, p, i32],
         'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
+        'gnssacq_search_grouped': [p, p, i32, i32, i32, i32, i32, i32, p, p, p],
         'gnssacq_mix': [p, p, i64, dbl, dbl],
         'gnssacq_preprocess': [p, p, i64, dbl, dbl, p, i32, dbl, i64, p],
         'gnssacq_set_replicas_from_chips': [p, p, i32, i32, i32, i32, dbl, dbl, i32, dbl],
@@ -202,6 +203,18 @@ class Engine:
                                              int(n_lags), _ptr(metric), _ptr(lag), _ptr(dbin),
                                              _ptr(q) if dump else None))
         return (metric, lag, dbin, q) if dump else (metric, lag, dbin)
+
+    def search_grouped(self, nco_freq, group_len, block_stride, n_blocks, normalize, n_lags=0):
+        """nco_freq = G consecutive groups of group_len entries; best per (group, replica).
+        Returns (metric, lag, dbin) of shape (G, R), dbin relative to its group."""
+        f = np.ascontiguousarray(nco_freq, dtype=np.float64)
+        G = f.size // int(group_len)
+        metric = np.empty((G, self.R), np.float32)
+        lag = np.empty((G, self.R), np.int32)
+        dbin = np.empty((G, self.R), np.int32)
+        self._check(self._lib.gnssacq_search_grouped(self._h, _ptr(f), f.size, int(group_len), int(block_stride), int(n_blocks),
+                                                     int(bool(normalize)), int(n_lags), _ptr(metric), _ptr(lag), _ptr(dbin)))
+        return metric, lag, dbin
 
     def search_device(self, nco_freq, block_stride, n_blocks, normalize, n_lags, device_records_ptr):
         f = np.ascontiguousarray(nco_freq, dtype=np.float64)

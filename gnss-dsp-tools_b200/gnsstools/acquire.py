@@ -181,12 +181,11 @@ def acquire(signal, x, keys, doppler_search, ms, engine=None, lag_limit=0, block
         eng.set_signal(np.ascontiguousarray(x[:need], dtype=np.complex64))
     out = []
     if sig.fdma:
+        # one batched call: the channels are Doppler groups of the same (channel-independent) replica
         set_replicas(eng, sig, [None])
-        for chan in keys:
-            f = -(sig.carrier_step * chan + bins) / sig.fs          # acquire-glonass-l1.py:28
-            metric, lag, dbin = eng.search(f, sig.n, B, sig.normalize, lag_limit)
-            out.append(_finish(sig, L, bins, metric[0], lag[0], dbin[0]))
-        return out
+        f = np.concatenate([-(sig.carrier_step * chan + bins) / sig.fs for chan in keys])   # acquire-glonass-l1.py:28
+        metric, lag, dbin = eng.search_grouped(f, len(bins), sig.n, B, sig.normalize, lag_limit)
+        return [_finish(sig, L, bins, metric[g, 0], lag[g, 0], dbin[g, 0]) for g in range(len(keys))]
     set_replicas(eng, sig, keys)
     f = -bins / sig.fs                                              # acquire-gps-l1.py:28
     metric, lag, dbin = eng.search(f, sig.n, B, sig.normalize, lag_limit)

@@ -99,6 +99,15 @@ int gnssacq_search_device(gnssacq_t* h, const double* nco_freq, int32_t D, int32
                           int32_t n_blocks, int32_t normalize, int32_t n_lags,
                           void* device_records);
 
+/* One call for a list of Doppler GROUPS: nco_freq holds D / group_len consecutive groups of
+ * group_len entries and the per-replica best is taken inside each group — the channel loop of the
+ * FDMA scripts (acquire-glonass-l1.py:26-39, 60-69: one search() per channel with
+ * w = nco(-(562500*chan+doppler)/fs), the replica being channel-independent) as a single batch.
+ * Outputs: R * (D / group_len) entries, entry g*R + r for group g and replica r; dbin counts from the
+ * start of the group (-1: nothing exceeded 0). */
+int gnssacq_search_grouped(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t group_len, int32_t block_stride,
+                           int32_t n_blocks, int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin);
+
 /* nco.mix(x, f, p) of gnsstools/nco.py:30-41 on the GPU, in place on a host complex64
  * buffer (copy in, mix, copy out). Bit-identical to the reference. */
 int gnssacq_mix(gnssacq_t* h, float* iq_c64, int64_t n_samples, double f, double p);

@@ -111,6 +111,10 @@ static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t = 0) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t hgt, int, cudaStream_t = 0) {
+  for (size_t i = 0; i < hgt; ++i) memcpy(static_cast<char*>(d) + i * dp, static_cast<const char*>(s) + i * sp, w);
+  return 0;
+}
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }

@@ -109,7 +109,21 @@ def test_errors(eng):
     with pytest.raises(ValueError):
         eng.search(np.array([0.0]), 64, 2, False)          # capture too short
     with pytest.raises(ValueError):
-        eng.set_replicas(np.ones((1, 2 * 37), np.float32))  # prime factor 37 unsupported
+        eng.set_replicas(np.ones((1, 2 * 300007), np.float32))  # not plannable and too long to embed (> 524288)
+
+
+@pytest.mark.parametrize('n,pad,boc,normalize,blocks,lag_limit', [(646, False, False, True, 2, None),       # 2*17*19 -> 2048 (one CTA)
+                                                                  (4522, True, False, False, 2, None),        # 2n = 4*7*17*19 -> 32768 (two kernels)
+                                                                  (4097, False, True, False, 1, 1000)])       # 17*241 -> 16384
+def test_any_length_runs_embedded_in_a_power_of_two(eng, n, pad, boc, normalize, blocks, lag_limit):
+    """Lengths the planner cannot factor (the reference takes any N through fftpack,
+    acquire-gps-l5i.py:24,32) run embedded in the next power of two >= 2N-1: periodically extended
+    replica, zero-padded blocks, lags 0..N-1 — same q grid, same indices, same mean."""
+    info = _case(eng, n, pad, boc, normalize, blocks, (-400, 400, 400), n * 1000.0, nprn=1, lag_limit=lag_limit)
+    N = 2 * n if pad else n
+    assert info['N'] >= 2 * N - 1 and info['N'] & (info['N'] - 1) == 0 and eng.kernel_variant() == 128
+    _case(eng, 4096, False, False, True, 1, (-1000, 1000, 500), 4.096e6)      # back to a plannable length
+    assert eng.kernel_variant() == 4
 
 
 # --------------------------------------------------------------------------- replica builder / correlator bank
@@ -255,3 +269,22 @@ def test_large_mixed_prime_factor_and_generic(eng):
     transform (11*16) has no specialisation and runs the generic Cooley-Tukey kernels."""
     info = _case(eng, 32736, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1)
     assert info['N1'] == 186 and info['N2'] == 176 and eng.kernel_variant() == (2 | 8)
+
+
+def test_grouped_search_equals_one_search_per_group(eng):
+    """gnssacq_search_grouped (the FDMA channel loop of acquire-glonass-l1.py:60-69 as one batch):
+    every group's records equal those of a separate search over that group's Doppler list."""
+    rng = np.random.default_rng(1)
+    n = 2048
+    x = (rng.normal(0, 8, 3 * n) + 1j * rng.normal(0, 8, 3 * n)).astype(np.complex64)
+    eng.set_signal(x)
+    eng.set_replicas(np.array([orc.replica(ca.ca_code(p), n, False, False) for p in (1, 2)]))
+    bins = np.arange(-3, 3) * 1e-4
+    groups = [bins + g * 0.01 for g in range(4)]
+    M, L, Dd = eng.search_grouped(np.concatenate(groups), len(bins), n, 2, True)
+    assert M.shape == (4, 2)
+    for g, f in enumerate(groups):
+        m, l, d = eng.search(f, n, 2, True)
+        assert np.array_equal(m, M[g]) and np.array_equal(l, L[g]) and np.array_equal(d, Dd[g])
+    with pytest.raises(ValueError):
+        eng.search_grouped(np.zeros(7), 3, n, 2, True)          # not a whole number of groups

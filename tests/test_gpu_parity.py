@@ -53,6 +53,9 @@ ENGINE_CASES = [
     ('cfg4-native-2x25000', 10230, 25000000.0, 25000, True, False, False, 4, (-400, 400, 200), 2, None),
     # BASELINE config 3 at its native rate: Galileo E1 (4092 chips, BOC(1,1)), 4 ms at 20.46 Msps, zero-padded 2n = 163680
     ('cfg3-native-2x81840-boc', 4092, 20460000.0, 81840, True, True, False, 1, (-100, 50, 50), 2, None),
+    # N = 2*17*19*61 = 39406: no plan (prime factors 17, 19, 61) -> embedded in 131072 >= 2N-1
+    ('any-length-39406-embedded', 1023, 3940600.0, 39406, False, False, True, 2, (-200, 200, 100), 2, None),
+    ('any-length-2x19703-padded', 1023, 1970300.0, 19703, True, False, False, 2, (-200, 200, 100), 1, None),
     # 32736 = 186 x 176: prime-factor specialised columns transform (31*6) with a generic Cooley-Tukey rows transform (11*16)
     ('mixed-32736-2ms', 1023, 16368000.0, 32736, False, False, True, 2, (-500, 500, 250), 2, None),
 ]
@@ -126,7 +129,7 @@ def test_all_zero_and_short_inputs(eng):
     with pytest.raises(ValueError):
         eng.search(np.array([0.0]), n, 3, True)     # needs 3 blocks, capture holds 2
     with pytest.raises(ValueError):
-        eng.set_replicas(np.ones((1, 2 * 37), np.float32))
+        eng.set_replicas(np.ones((1, 2 * 300007), np.float32))    # not plannable and too long to embed
 
 
 @pytest.mark.parametrize('n', [4096, 16384, 61380, 163680])

@@ -19,7 +19,9 @@ stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
 rng = np.random.default_rng(0)
-which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+quick = 'quick' in sys.argv[1:]
+args = [a for a in sys.argv[1:] if a != 'quick']
+which = args[0] if args else 'all'
 
 CASES = [('cfg2 163680 R32 D80 B1', 163680, False, 32, 80, 1, True),
          ('cfg4 61380 R64 D70 B20', 30690, True, 64, 70, 20, False),
@@ -60,8 +62,10 @@ for name, n, pad, R, D, B, norm in CASES:
     base = dict(v3=0, v3_rows=0, v3_cols=0, v3_rc=0, v3_g=0, lanes=2)
     ref = run(name, n, pad, R, D, B, norm, base)
     nrows = 4 if N == 163680 else 2
-    ncols = 3 if N == 163680 else 2
-    shapes = [(0, 0), (8, 4), (4, 8), (32, 4), (16, 8), (32, 2)] if B == 1 else [(0, 0), (8, 1), (16, 1), (32, 1)]
+    ncols = 2
+    if quick:
+        nrows, ncols = 1, 2
+    shapes = [(0, 0), (16, 4), (32, 4), (32, 8), (16, 16), (8, 16)] if B == 1 else [(0, 0), (16, 1), (32, 1), (64, 1)]
     # tile shapes at the default chunk shape
     for rv, cv in itertools.product(range(nrows), range(ncols)):
         got = run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rows=rv, v3_cols=cv))
