@@ -11,6 +11,8 @@
 #include <cuda.h>
 #endif
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <functional>
 #include <new>
@@ -79,6 +81,9 @@ struct gnssacq {
   CubeTw cube_tw{nullptr, nullptr};
   DevBuf d_C;                         // replica spectra [R][N]
   int R = 0, N = 0;
+  void* nccl_comm = nullptr;          // ncclComm_t of gnssacq_nccl_init (NCCL is bound at run time, see NcclApi)
+  int nccl_rank = 0, nccl_world = 1;
+  DevBuf d_allrec, d_merged;
   int embed_n = 0;                    // != 0: the caller's transform length, embedded in the planned length N (>= 2*embed_n - 1)
 
   DevBuf d_X, d_scratch, d_parts, d_freq, d_rec, d_q, d_tmp;
@@ -643,8 +648,111 @@ int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned lo
 #endif
 }  // namespace acq
 
+// ---------------------------------------------------------------- NCCL, bound at run time
+// libgnssacq.so does not link against libnccl: the all-gather of the sharded search resolves the
+// few entry points it needs with dlopen/dlsym when gnssacq_nccl_init is first called (inside a
+// PyTorch process that is the NCCL PyTorch already loaded), so single-GPU users need no NCCL at all.
+namespace {
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_api(NcclApi** out) {
+  if (!g_nccl.lib) {
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(GNSSACQ_ESTATE, std::string("NCCL is not available: ") + dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(g_nccl.lib, "ncclAllGather"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+      g_nccl = NcclApi();
+      return fail(GNSSACQ_ESTATE, "libnccl lacks an expected entry point");
+    }
+  }
+  *out = &g_nccl;
+  return 0;
+}
+int nccl_fail(const NcclApi* api, const char* what, int rc) {
+  return fail(GNSSACQ_ECUDA, std::string(what) + ": " + (api->GetErrorString ? api->GetErrorString(rc) : "NCCL error") + " (" + std::to_string(rc) + ")");
+}
+}  // namespace
+
 // =============================================================================== C ABI
 extern "C" {
+
+int gnssacq_nccl_unique_id(void* id128) {
+  if (!id128) return fail(GNSSACQ_EINVAL, "NULL argument");
+  NcclApi* api;
+  if (int rc = nccl_api(&api)) return rc;
+  NcclUniqueId id;
+  if (int rc = api->GetUniqueId(&id)) return nccl_fail(api, "ncclGetUniqueId", rc);
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int gnssacq_nccl_init(gnssacq_t* h, const void* id128, int32_t rank, int32_t world) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(GNSSACQ_EINVAL, "bad communicator arguments");
+  NcclApi* api;
+  if (int rc = nccl_api(&api)) return rc;
+  CU(cudaSetDevice(h->device));
+  if (h->nccl_comm) { api->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  if (int rc = api->CommInitRank(&h->nccl_comm, world, id, rank)) { h->nccl_comm = nullptr; return nccl_fail(api, "ncclCommInitRank", rc); }
+  h->nccl_rank = rank;
+  h->nccl_world = world;
+  return 0;
+}
+
+int gnssacq_search_sharded(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride, int32_t n_blocks,
+                           int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin) {
+  if (!h || !nco_freq || !metric || !lag || !dbin || D <= 0) return fail(GNSSACQ_EINVAL, "bad search arguments");
+  CU(cudaSetDevice(h->device));
+  if (h->R <= 0) return fail(GNSSACQ_ESTATE, "gnssacq_set_replicas has not been called");
+  const int world = h->nccl_comm ? h->nccl_world : 1, rank = h->nccl_comm ? h->nccl_rank : 0;
+  const int R = h->R;
+  const int base = D / world, extra = D % world;
+  const int lo = rank * base + std::min(rank, extra), cnt = base + (rank < extra ? 1 : 0);
+  if (int rc = h->d_rec.ensure((size_t)R * sizeof(Record))) return rc;
+  if (int rc = h->d_allrec.ensure((size_t)world * R * sizeof(Record))) return rc;
+  if (int rc = h->d_merged.ensure((size_t)R * sizeof(Record))) return rc;
+  if (cnt > 0) {
+    if (int rc = run_search(h, nco_freq + lo, cnt, block_stride, n_blocks, normalize, n_lags, h->d_rec.as<Record>(), nullptr)) return rc;
+  } else {
+    std::vector<Record> none(R);
+    for (auto& r : none) { r.metric = 0.f; r.lag = 0; r.dbin = -1; r.pad = 0; }
+    CU(cudaMemcpyAsync(h->d_rec.p, none.data(), none.size() * sizeof(Record), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (world > 1) {
+    NcclApi* api;
+    if (int rc = nccl_api(&api)) return rc;
+    if (int rc = api->AllGather(h->d_rec.p, h->d_allrec.p, (size_t)R * 4, /*ncclInt32*/ 2, h->nccl_comm, h->stream))
+      return nccl_fail(api, "ncclAllGather", rc);
+  } else {
+    CU(cudaMemcpyAsync(h->d_allrec.p, h->d_rec.p, (size_t)R * sizeof(Record), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  GNSSACQ_LAUNCH(k_merge_records, dim3((R + 127) / 128), dim3(128), 0, h->stream, h->d_allrec.as<Record>(), world, R, D, h->d_merged.as<Record>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  std::vector<Record> rec(R);
+  CU(cudaMemcpyAsync(rec.data(), h->d_merged.p, rec.size() * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < R; ++r) { metric[r] = rec[r].metric; lag[r] = rec[r].lag; dbin[r] = rec[r].dbin; }
+  return 0;
+}
+
 
 const char* gnssacq_last_error(void) { return g_err.c_str(); }
 
@@ -687,7 +795,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint, &h->d_repext})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint, &h->d_repext, &h->d_allrec, &h->d_merged})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -696,6 +804,7 @@ int gnssacq_destroy(gnssacq_t* h) {
     if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
     h->d_scratch_lane[l].release();
   }
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

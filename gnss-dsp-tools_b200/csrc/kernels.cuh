@@ -388,6 +388,28 @@ k_finalize(const Part* __restrict__ parts, int D, int Dg, int ntiles, int N, int
   }
 }
 
+// Rank-ordered merge of Doppler-sharded records (all: [world][R], rank k owning the bins that start
+// at off(k) = k*(D/world) + min(k, D%world)): a later rank replaces the best only on a strictly
+// greater metric, so ties go to the lowest Doppler bin exactly as the reference's ascending scan
+// (acquire-gps-l1.py:26,36-39). Identical on every rank.
+static __global__ void __launch_bounds__(128)
+k_merge_records(const Record* __restrict__ all, int world, int R, int D, Record* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int base = D / world, extra = D % world;
+  Record best = all[r];
+  if (best.dbin < 0) { best.metric = 0.f; best.lag = 0; best.dbin = -1; }
+  for (int k = 1; k < world; ++k) {
+    Record rec = all[(long long)k * R + r];
+    if (rec.dbin >= 0 && rec.metric > best.metric) {
+      rec.dbin += k * base + (k < extra ? k : extra);
+      best = rec;
+    }
+  }
+  best.pad = 0;
+  out[r] = best;
+}
+
 // int8 replicas (+-1 / 0) -> float32: lets callers ship a quarter of the bytes over PCIe.
 static __global__ void __launch_bounds__(kThreads)
 k_i8_to_f32(const signed char* __restrict__ in, long long n, float* __restrict__ out) {

@@ -45,6 +45,9 @@ def _declare(lib):
         'gnssacq_search': [p, p, i32, i32, i32, i32, i32, p, p, p, p],
         'gnssacq_search_device': [p, p, i32, i32, i32, i32, i32, p],
         'gnssacq_search_grouped': [p, p, i32, i32, i32, i32, i32, i32, p, p, p],
+        'gnssacq_nccl_unique_id': [p],
+        'gnssacq_nccl_init': [p, p, i32, i32],
+        'gnssacq_search_sharded': [p, p, i32, i32, i32, i32, i32, p, p, p],
         'gnssacq_mix': [p, p, i64, dbl, dbl],
         'gnssacq_preprocess': [p, p, i64, dbl, dbl, p, i32, dbl, i64, p],
         'gnssacq_set_replicas_from_chips': [p, p, i32, i32, i32, i32, dbl, dbl, i32, dbl],
@@ -214,6 +217,28 @@ class Engine:
         dbin = np.empty((G, self.R), np.int32)
         self._check(self._lib.gnssacq_search_grouped(self._h, _ptr(f), f.size, int(group_len), int(block_stride), int(n_blocks),
                                                      int(bool(normalize)), int(n_lags), _ptr(metric), _ptr(lag), _ptr(dbin)))
+        return metric, lag, dbin
+
+    # -- multi-GPU through the C ABI (NCCL inside the library; no torch needed)
+    def nccl_unique_id(self):
+        """128-byte ncclUniqueId: create on one rank, pass to every rank's nccl_init."""
+        buf = C.create_string_buffer(128)
+        self._check(self._lib.gnssacq_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_init(self, unique_id, rank, world):
+        if len(unique_id) != 128:
+            raise ValueError('ncclUniqueId is 128 bytes')
+        self._check(self._lib.gnssacq_nccl_init(self._h, C.c_char_p(bytes(unique_id)), int(rank), int(world)))
+
+    def search_sharded(self, nco_freq, block_stride, n_blocks, normalize, n_lags=0):
+        """Collective: every rank passes the full Doppler list and gets the single-GPU answer."""
+        f = np.ascontiguousarray(nco_freq, dtype=np.float64)
+        metric = np.empty(self.R, np.float32)
+        lag = np.empty(self.R, np.int32)
+        dbin = np.empty(self.R, np.int32)
+        self._check(self._lib.gnssacq_search_sharded(self._h, _ptr(f), f.size, int(block_stride), int(n_blocks), int(bool(normalize)),
+                                                     int(n_lags), _ptr(metric), _ptr(lag), _ptr(dbin)))
         return metric, lag, dbin
 
     def search_device(self, nco_freq, block_stride, n_blocks, normalize, n_lags, device_records_ptr):

@@ -108,6 +108,24 @@ int gnssacq_search_device(gnssacq_t* h, const double* nco_freq, int32_t D, int32
 int gnssacq_search_grouped(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t group_len, int32_t block_stride,
                            int32_t n_blocks, int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin);
 
+/* Multi-GPU, one process (and one handle) per GPU — the reference's only parallelism is
+ * mp.Pool over PRNs on one host (acquire-gps-l1.py:105-108); here the Doppler list is split into
+ * contiguous ascending shards and the per-replica records are exchanged with ONE all-gather.
+ * NCCL is bound at run time (dlopen "libnccl.so.2"), the library does not link against it.
+ *   gnssacq_nccl_unique_id   128-byte ncclUniqueId; create it on one rank and hand it to the others
+ *                            by any means (file, socket, MPI, torch.distributed).
+ *   gnssacq_nccl_init        collective over all ranks: joins this handle's device to the communicator.
+ *   gnssacq_search_sharded   collective: rank k searches bins [k*D/world ...) of the SAME nco_freq
+ *                            list every rank passes, all-gather of R 16-byte records on the handle's
+ *                            stream, then a device merge in rank order (strict '>': ties go to the
+ *                            lowest bin, as the reference's ascending scan) — every rank returns the
+ *                            single-GPU answer, dbin indexing the full list. Without a communicator
+ *                            it is gnssacq_search. */
+int gnssacq_nccl_unique_id(void* id128);
+int gnssacq_nccl_init(gnssacq_t* h, const void* id128, int32_t rank, int32_t world);
+int gnssacq_search_sharded(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t block_stride, int32_t n_blocks,
+                           int32_t normalize, int32_t n_lags, float* metric, int32_t* lag, int32_t* dbin);
+
 /* nco.mix(x, f, p) of gnsstools/nco.py:30-41 on the GPU, in place on a host complex64
  * buffer (copy in, mix, copy out). Bit-identical to the reference. */
 int gnssacq_mix(gnssacq_t* h, float* iq_c64, int64_t n_samples, double f, double p);

@@ -12,4 +12,4 @@ for k in 0 1 2 3 4 5 6 7 8 9; do
   g++ $flags -DGNSSACQ_REG_PART=$k -c -x c++ "$root/gnss-dsp-tools_b200/csrc/registry.cu" -o "$obj/registry_$k.o" &
 done
 wait
-g++ -shared -pthread "$obj"/*.o -o "$here/libgnssacq_emu.so"
+g++ -shared -pthread "$obj"/*.o -o "$here/libgnssacq_emu.so" -ldl

@@ -4,7 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo
 //        -DSCOLS=S372 -DSROWS=S440 -DNFFT=163680 -o corr_pipe tools/microbench/corr_pipe.cu
 #include "../../gnss-dsp-tools_b200/csrc/fft_plan.h"
-#include "../../gnss-dsp-tools_b200/csrc/kernels_pipe.cuh"
+#include "kernels_pipe.cuh"
 #include <cstdio>
 #include <cstring>
 #include <random>

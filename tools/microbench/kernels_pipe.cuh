@@ -14,7 +14,7 @@
 // time (profiles/README.md, r02). Kept for tools/microbench/corr_pipe.cu; the small-CTA kernels
 // in kernels_small.cuh are what came out of the comparison.
 #pragma once
-#include "kernels_small.cuh"
+#include "../../gnss-dsp-tools_b200/csrc/kernels_small.cuh"
 
 namespace acq {
 
