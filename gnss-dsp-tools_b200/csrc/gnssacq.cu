@@ -100,6 +100,9 @@ struct gnssacq {
   int v3_rows_variant = 0, v3_cols_variant = 0;      // tile shapes (registry.cu), A/B
   int v3_rc = 0, v3_g = 0;                           // replicas x Doppler bins per launch (0 = automatic)
   DevBuf d_v3tab;                                    // padded column table + tile origins
+  bool use_fused = true;                             // one persistent kernel per Doppler chunk (kernels_fused.cuh) instead of the pair
+  int fused_rc = 0, fused_g = 0, fused_sets = 3, fused_ctas = 0;   // group shape, scratch ring depth, CTAs per SM (0 = automatic)
+  DevBuf d_fsync;                                    // ticket, error flag, per-group counters
   DevBuf d_hint;                                     // per (replica, Doppler) unit: best value reported so far (peak-search floor)
   int v3tab_key[4] = {0, 0, 0, 0};                   // (N, RB, PB, CW) the table was built for
   int v3_ntiles = 0;
@@ -327,6 +330,7 @@ struct V3Setup {
   bool on = false;
   RowsV3 r{};
   ColsV3 c{};
+  FusedKernel f{};                  // f.fn != nullptr: the fused persistent kernel runs instead of the pair
   int ntiles = 0, NP = 0, F1 = 0, F2 = 0;
 };
 
@@ -338,6 +342,13 @@ V3Setup v3_setup(const gnssacq* h, bool multi, bool dump) {
   v.c = find_cols_v3(h->dp.s1, multi, dump, h->v3_cols_variant);
   if (!v.r.fn || !v.c.fn) return v;
   if (v.r.smem > h->smem_optin || v.c.smem > h->smem_optin) return v;
+  if (h->use_fused) {
+    v.f = find_fused(h->dp.s1, h->dp.s2, multi, dump);
+    if (v.f.fn && v.f.smem <= h->smem_optin) {          // the fused kernel fixes the tile shapes
+      v.r.T = v.f.T; v.r.RA = v.f.RA; v.r.RB = v.f.RB; v.r.PB = v.f.PB;
+      v.c.CW = v.f.CW;
+    } else v.f = FusedKernel{};
+  }
   v.NP = v.r.RA * v.r.PB;
   v.ntiles = (v.r.RB % v.c.CW == 0) ? v.r.RA * (v.r.RB / v.c.CW) : (v.NP + v.c.CW - 1) / v.c.CW;
   // tensor-map boxes are limited to 256 per dimension: N1 = F1 * F2 with the largest F1 <= 256
@@ -443,6 +454,55 @@ int correlate_chunk_v3(gnssacq* h, const V3Setup& v, int B, int D, int d0, int d
       CU(cudaEventRecord(h->ev_join[l], h->lane[l]));
       CU(cudaStreamWaitEvent(h->stream, h->ev_join[l], 0));
     }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// The whole correlate stage of a Doppler chunk as one persistent launch (kernels_fused.cuh).
+int correlate_fused(gnssacq* h, const V3Setup& v, int B, int D, int d0, int dc, int n_lags, float scale, float* d_qdump) {
+  const DevPlan& p = h->dp;
+  FusedJob job{};
+  job.R = h->R; job.dc = dc; job.B = B;
+  // group = Rc replicas x G bins x B blocks; about 16 unit-blocks per scratch set keeps three sets (and the
+  // replica spectra) inside L2
+  job.G = h->fused_g > 0 ? h->fused_g : std::max(1, 4 / B);
+  job.G = std::max(1, std::min(job.G, dc));
+  job.Rc = h->fused_rc > 0 ? h->fused_rc : std::max(1, 16 / (job.G * B));
+  job.Rc = std::max(1, std::min(job.Rc, h->R));
+  job.ngr = (h->R + job.Rc - 1) / job.Rc;
+  job.ng = job.ngr * ((dc + job.G - 1) / job.G);
+  job.nrt = (p.N1 + v.f.T - 1) / v.f.T;
+  job.ntiles = v.ntiles;
+  job.nsets = std::max(2, std::min(h->fused_sets, 8));
+  job.slots_per_set = job.Rc * job.G * B;
+  job.nR = job.nrt * job.Rc;
+  job.nC = job.ntiles * job.Rc * job.G;
+  job.D = D; job.d0 = d0; job.n_lags = n_lags; job.zmul = v.F2; job.scale = scale;
+  if ((long long)job.ng * (job.nR + job.nC) > 0x7fffffffll) return fail(GNSSACQ_EINVAL, "too many tasks for one fused launch");
+  const long long slots = (long long)job.nsets * job.slots_per_set;
+  const size_t sbytes = (size_t)slots * p.N1 * v.NP * sizeof(float2);
+  if (int rc = v3_upload_tables(h, v)) return rc;
+  if (int rc = h->d_scratch.ensure(sbytes)) return rc;
+  if (int rc = v3_map_for(h, v, gnssacq::kMaxLanes, h->d_scratch.p, slots)) return rc;
+  const size_t nsync = 2 + 2 * (size_t)job.ng;
+  if (int rc = h->d_fsync.ensure(nsync * sizeof(int))) return rc;
+  CU(cudaMemsetAsync(h->d_fsync.p, 0, nsync * sizeof(int), h->stream));
+  FusedSync sy;
+  sy.ticket = h->d_fsync.as<int>();
+  sy.error = sy.ticket + 1;
+  sy.rows_done = sy.ticket + 2;
+  sy.cols_done = sy.rows_done + job.ng;
+  if (int rc = allow_smem(h, v.f.fn, v.f.smem)) return rc;
+  DevPlan pv = p;
+  pv.col_lag = h->d_v3tab.as<int>();
+  const int* tile_col0 = h->d_v3tab.as<int>() + v.NP + 2 * v.c.CW;
+  const int ctas = h->fused_ctas > 0 ? h->fused_ctas : v.f.ctas_per_sm;
+  const long long total = (long long)job.ng * (job.nR + job.nC);
+  const int grid = (int)std::min<long long>(total, (long long)h->num_sms * ctas);
+  StageTimer timer(h, kStageCorrCols, 1);
+  GNSSACQ_LAUNCH(v.f.fn, dim3(grid), dim3(v.f.threads), v.f.smem, h->stream, pv, h->v3_map[gnssacq::kMaxLanes].map, tile_col0, job, sy,
+                 h->d_X.as<float2>(), h->d_C.as<float2>(), h->d_scratch.as<float2>(), h->d_parts.as<Part>(), d_qdump, h->d_hint.as<unsigned>());
+  h->launches += 1;
   CU(cudaGetLastError());
   return 0;
 }
@@ -594,7 +654,9 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   for (int d0 = 0; d0 < D; d0 += Dc) {
     const int dc = std::min(Dc, D - d0);
     if (int rc = forward<0>(h, nullptr, h->d_freq.as<double>() + d0, stride, B, dc * B, h->d_X.as<float2>())) return rc;
-    if (v3.on) {
+    if (v3.on && v3.f.fn) {
+      if (int rc = correlate_fused(h, v3, B, D, d0, dc, n_lags, scale, d_qdump)) return rc;
+    } else if (v3.on) {
       if (int rc = correlate_chunk_v3(h, v3, B, D, d0, dc, n_lags, scale, d_qdump)) return rc;
     } else if (int rc = correlate_chunk(h, B, D, d0, dc, Uc, n_lags, scale, ntiles, d_qdump)) return rc;
   }
@@ -795,7 +857,7 @@ int gnssacq_destroy(gnssacq_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
-                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint, &h->d_repext, &h->d_allrec, &h->d_merged})
+                    &h->d_y1, &h->d_z, &h->d_fir, &h->d_pre128, &h->d_chips, &h->d_base, &h->d_bank, &h->d_v3tab, &h->d_hint, &h->d_repext, &h->d_allrec, &h->d_merged, &h->d_fsync})
     b->release();
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -983,6 +1045,11 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
     return 0;
   }
   if (std::string(name) == "v3") { h->use_v3 = value != 0; return 0; }
+  if (std::string(name) == "fused") { h->use_fused = value != 0; return 0; }
+  if (std::string(name) == "fused_rc") { h->fused_rc = value; return 0; }
+  if (std::string(name) == "fused_g") { h->fused_g = value; return 0; }
+  if (std::string(name) == "fused_sets") { h->fused_sets = value; return 0; }
+  if (std::string(name) == "fused_ctas") { h->fused_ctas = value; return 0; }
   if (std::string(name) == "v3_rows") { h->v3_rows_variant = value; return 0; }
   if (std::string(name) == "v3_cols") { h->v3_cols_variant = value; return 0; }
   if (std::string(name) == "v3_rc") { h->v3_rc = value; return 0; }
@@ -1173,7 +1240,7 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
   if (h->hp.cube && h->use_spec) return 4;
   if (!h->hp.large || !h->use_spec) return 0;
   return (find_rows_kernel(h->dp.s2, h->hp.gt) ? 1 : 0) | (find_cols_kernel(h->dp.s1, false) ? 2 : 0) | (h->hp.s1.pfa ? 8 : 0) | (h->hp.s2.pfa ? 16 : 0) |
-         (h->hp.gt ? 32 : 0) | (v3_setup(h, false, false).on ? 64 : 0);
+         (h->hp.gt ? 32 : 0) | (v3_setup(h, false, false).on ? 64 : 0) | (v3_setup(h, false, false).f.fn ? 256 : 0);
 }
 
 int gnssacq_synchronize(gnssacq_t* h) {

@@ -47,6 +47,25 @@ __host__ __device__ __forceinline__ int v3_slot(const ChunkV3& ck, int B, int r,
   return ((r - ck.r0) * ck.G + (dd - ck.dd0)) * B + b;
 }
 
+// One launch of the fused persistent correlate kernel (kernels_fused.cuh) and its global counters.
+struct FusedJob {
+  int R, dc, B;                 // replicas, Doppler bins of this chunk, non-coherent blocks
+  int Rc, G;                    // group shape: replicas x Doppler bins
+  int ngr, ng;                  // replica groups per Doppler group; number of groups
+  int nrt, ntiles;              // row tiles, column tiles
+  int nsets, slots_per_set;     // scratch ring: sets of Rc*G*B unit-block slots
+  int nR, nC;                   // rows / columns tickets per group (fixed; tickets past a ragged edge are empty)
+  int D, d0, n_lags, zmul;
+  float scale;
+};
+
+struct FusedSync {
+  int* ticket;                  // next ticket
+  int* rows_done;               // [ng]
+  int* cols_done;               // [ng]
+  int* error;                   // set when a wait gave up
+};
+
 // Per-(replica, doppler, tile) partial result of the correlate kernel.
 struct Part {
   unsigned long long key;   // (float bits of max q) << 32 | (0xffffffff - lag): max key = max q, ties -> lowest lag

@@ -42,6 +42,34 @@ template <class S, int T, int XBUFS> __host__ __device__ constexpr size_t rows_v
   return (size_t)XBUFS * T * S::F * sizeof(float2) + 2 * (size_t)T * S::radix(0) * v3_pitch(S::radix(1)) * sizeof(float2) + XBUFS * 8;
 }
 
+// Stage A of one rows tile: this thread's butterfly (row ra, contiguous digit b) — multiply the
+// spectra tile by the replica values held in registers, radix-RA inverse butterfly over the
+// stride-RB digit, scatter into the padded exchange tile.
+template <class S>
+__device__ __forceinline__ void rows_v3_stage_a(const float2* __restrict__ xtile, float2* __restrict__ et, const float2* c, int ra, int b) {
+  constexpr int N2 = S::F, RA = S::radix(0), RB = S::radix(1), PB = v3_pitch(RB), NP = RA * PB;
+  const float2* xp = xtile + ra * N2 + b;
+  float2 y[RA];
+#pragma unroll
+  for (int a = 0; a < RA; ++a) y[a] = cmulc(c[a], xp[a * RB]);
+  inv_dft<RA>(y);
+  float2* ep = et + ra * NP + b;
+#pragma unroll
+  for (int a = 0; a < RA; ++a) ep[a * PB] = y[a];
+}
+// Stage B: radix-RB inverse butterfly of group `grp` (= row * RA + a') in place, 16-byte accesses.
+template <class S>
+__device__ __forceinline__ void rows_v3_stage_b(float2* __restrict__ et, int grp) {
+  constexpr int RB = S::radix(1), PB = v3_pitch(RB);
+  float4* p4 = reinterpret_cast<float4*>(et + grp * PB);
+  float2 v[RB];
+#pragma unroll
+  for (int q = 0; q < RB / 2; ++q) { const float4 t = p4[q]; v[2 * q] = make_float2(t.x, t.y); v[2 * q + 1] = make_float2(t.z, t.w); }
+  inv_dft<RB>(v);
+#pragma unroll
+  for (int q = 0; q < RB / 2; ++q) p4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+}
+
 // grid = (row tiles, Rc, splits of the pair list); THREADS >= T * RB. X: [Dc][B][N], C: [R][N] (position order), scratch as above.
 template <class S, int T, int THREADS, int MINCTAS, int XBUFS>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
@@ -93,26 +121,11 @@ k_corr_rows_v3(DevPlan pl, const float2* __restrict__ X, const float2* __restric
     const int xs = it % XBUFS, e = it & 1;
     float2* et = ebuf + e * ET;
     mbar_wait(&full[xs], (unsigned)(it / XBUFS) & 1u);
-    if (act_a) {
-      const float2* xp = xbuf + xs * XT + ra * N2 + b;
-      float2 y[RA];
-#pragma unroll
-      for (int a = 0; a < RA; ++a) y[a] = cmulc(c[a], xp[a * RB]);
-      inv_dft<RA>(y);
-      float2* ep = et + ra * NP + b;
-#pragma unroll
-      for (int a = 0; a < RA; ++a) ep[a * PB] = y[a];
-    }
+    if (act_a) rows_v3_stage_a<S>(xbuf + xs * XT, et, c, ra, b);
     __syncthreads();                                           // exchange tile complete; ring slot xs drained
     if (tid == 0 && it + XBUFS < nit) { fence_async_smem(); issue(it + XBUFS); }
     if (act_b) {
-      float4* p4 = reinterpret_cast<float4*>(et + tid * PB);
-      float2 v[RB];
-#pragma unroll
-      for (int q = 0; q < RB / 2; ++q) { const float4 t = p4[q]; v[2 * q] = make_float2(t.x, t.y); v[2 * q + 1] = make_float2(t.z, t.w); }
-      inv_dft<RB>(v);
-#pragma unroll
-      for (int q = 0; q < RB / 2; ++q) p4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+      rows_v3_stage_b<S>(et, tid);
       fence_async_smem();                                      // these writes are read by the bulk store below
     }
     if (tid == 0) bulk_wait_read<0>();                         // the store of pair it-1 has drained the other exchange buffer
@@ -235,6 +248,23 @@ __device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, cons
   }
 }
 
+// First inverse stage of a columns tile [N1][CW]: radix(1) at unit stride, in place.
+template <class S, int CW, int THREADS>
+__device__ __forceinline__ void cols_v3_first(float2* tile) {
+  constexpr int R = S::radix(1), nbf = S::F / R, nb = THREADS / CW;
+  const int tc = threadIdx.x & (CW - 1), tb = threadIdx.x / CW;
+#pragma unroll 1
+  for (int bf = tb; bf < nbf; bf += nb) {
+    float2* p = tile + bf * R * CW + tc;
+    float2 v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = p[q * CW];
+    inv_dft<R>(v);
+#pragma unroll
+    for (int q = 0; q < R; ++q) p[q * CW] = v[q];
+  }
+}
+
 // Persistent: task t = blockIdx.x + k * gridDim.x = (unit ul of the chunk, column tile ct), B items each.
 // map: 8-byte elements, dims (NP, F1, F2 * slots), box (CW, F1, F2) with N1 = F1 * F2; zmul = F2.
 // pl.col_lag must point at the padded column table (NP + slack entries, -1 = pad column).
@@ -291,19 +321,7 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     float* qd = DUMP ? q_dump + unit * N : nullptr;
     float2* tile = smem + (seq & 1) * SLOT;
     mbar_wait(&full[seq & 1], (seq >> 1) & 1u);
-    {                                                          // first inverse stage: unit stride, in place
-      constexpr int R = S::radix(1), nbf = N1 / R;
-#pragma unroll 1
-      for (int bf = tb; bf < nbf; bf += nb) {
-        float2* p = tile + bf * R * CW + tc;
-        float2 v[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = p[q * CW];
-        inv_dft<R>(v);
-#pragma unroll
-        for (int q = 0; q < R; ++q) p[q * CW] = v[q];
-      }
-    }
+    cols_v3_first<S, CW, THREADS>(tile);
     __syncthreads();
     if (lagc >= 0) cols_v3_last<S, MULTI, DUMP, CW, THREADS>(tile, qs, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
     if (last) {

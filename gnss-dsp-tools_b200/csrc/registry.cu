@@ -4,6 +4,7 @@
 #include "registry.h"
 #include "kernels_small.cuh"
 #include "kernels_v3.cuh"
+#include "kernels_fused.cuh"
 
 namespace acq {
 
@@ -124,8 +125,21 @@ ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
 #undef PICK
   return ColsV3{nullptr, 0, 0, 0, 0};
 }
+#elif GNSSACQ_REG_PART == 10
+FusedKernel find_fused(const SubPlan& s1, const SubPlan& s2, bool multi, bool dump) {
+#define PICK(SC, SR, T, CW, TH, C, M, DUMP) \
+  FusedKernel{k_corr_fused<SR, SC, T, CW, M, DUMP, TH, C>, TH, T, CW, C, fused_smem<SR, SC, T, CW, M>(), SR::radix(0), SR::radix(1), v3_pitch(SR::radix(1))}
+#define TRY(SC, SR, T, CW, TH, C)                                                                                  \
+  if (schedule_matches<SC>(s1) && schedule_matches<SR>(s2))                                                        \
+    return multi ? (dump ? PICK(SC, SR, T, CW, TH, C, true, true) : PICK(SC, SR, T, CW, TH, C, true, false))       \
+                 : (dump ? PICK(SC, SR, T, CW, TH, C, false, true) : PICK(SC, SR, T, CW, TH, C, false, false));
+  TRY(S341, S480, 4, 8, 128, 4) TRY(S279, S220, 8, 8, 160, 3)
+#undef TRY
+#undef PICK
+  return FusedKernel{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+}
 #else
-#error "GNSSACQ_REG_PART must be 0..9"
+#error "GNSSACQ_REG_PART must be 0..10"
 #endif
 
 }  // namespace acq

@@ -37,4 +37,9 @@ struct ColsV3 { cols_v3_fn fn; int threads, CW, ctas_per_sm; size_t smem; };
 RowsV3 find_rows_v3(const SubPlan& s2, int variant);
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant);   // dump: also writes the q grid (tests)
 
+// Fused persistent correlate kernel (kernels_fused.cuh): both task types in one launch per Doppler chunk.
+typedef void (*fused_fn)(DevPlan, const TensorMap, const int*, FusedJob, FusedSync, const float2*, const float2*, float2*, Part*, float*, unsigned*);
+struct FusedKernel { fused_fn fn; int threads, T, CW, ctas_per_sm; size_t smem; int RA, RB, PB; };
+FusedKernel find_fused(const SubPlan& s1, const SubPlan& s2, bool multi, bool dump);
+
 }  // namespace acq

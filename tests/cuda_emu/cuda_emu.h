@@ -50,6 +50,7 @@ extern thread_local int emu_lane, emu_warp;
 struct EmuWarp { uint64_t slot[32]; std::barrier<>* bar; };
 extern EmuWarp* emu_warps;
 
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warps[emu_warp].bar->arrive_and_wait(); }
 

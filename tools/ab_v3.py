@@ -59,7 +59,7 @@ for name, n, pad, R, D, B, norm in CASES:
         rep[:, n:] = 0
     eng.set_signal(x)
     eng.set_replicas(rep)
-    base = dict(v3=0, v3_rows=0, v3_cols=0, v3_rc=0, v3_g=0, lanes=2)
+    base = dict(v3=0, fused=0, v3_rows=0, v3_cols=0, v3_rc=0, v3_g=0, lanes=2)
     ref = run(name, n, pad, R, D, B, norm, base)
     nrows = 4 if N == 163680 else 2
     ncols = 2
@@ -67,10 +67,21 @@ for name, n, pad, R, D, B, norm in CASES:
         nrows, ncols = 1, 2
     shapes = [(0, 0), (16, 4), (32, 4), (32, 8), (16, 16), (8, 16)] if B == 1 else [(0, 0), (16, 1), (32, 1), (64, 1)]
     # tile shapes at the default chunk shape
-    for rv, cv in itertools.product(range(nrows), range(ncols)):
+    for rv, cv in ([] if quick else itertools.product(range(nrows), range(ncols))):
         got = run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rows=rv, v3_cols=cv))
         if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
             print('   !! lags differ from the register-loading kernels')
+    # the fused persistent kernel: group shapes, ring depth, CTAs per SM
+    fshapes = [(0, 0), (4, 4), (2, 4), (8, 2), (4, 2), (8, 4), (16, 1)] if B == 1 else [(0, 0), (1, 1), (2, 1), (4, 1)]
+    for (rc, g), sets, ctas in itertools.product(fshapes, (2, 3, 4), (0,)):
+        got = run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=rc, fused_g=g, fused_sets=sets, fused_ctas=ctas))
+        if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
+            print('   !! lags differ from the register-loading kernels')
+    for ctas in (2, 3, 5):
+        run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=0, fused_g=0, fused_sets=3, fused_ctas=ctas))
+    run(name, n, pad, R, D, B, norm, dict(v3=1, fused=0, fused_rc=0, fused_g=0, fused_sets=3, fused_ctas=0))
+    if quick:
+        continue
     # chunk shapes and lanes at the default tiles
     for (rc, g), lanes in itertools.product(shapes, (2, 3)):
         run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rc=rc, v3_g=g, lanes=lanes))
