@@ -100,8 +100,10 @@ struct gnssacq {
   int v3_rows_variant = 0, v3_cols_variant = 0;      // tile shapes (registry.cu), A/B
   int v3_rc = 0, v3_g = 0;                           // replicas x Doppler bins per launch (0 = automatic)
   DevBuf d_v3tab;                                    // padded column table + tile origins
-  bool use_fused = true;                             // one persistent kernel per Doppler chunk (kernels_fused.cuh) instead of the pair
-  int fused_rc = 0, fused_g = 0, fused_sets = 3, fused_ctas = 0;   // group shape, scratch ring depth, CTAs per SM (0 = automatic)
+  // one persistent kernel per Doppler chunk (kernels_fused.cuh) instead of the pair: correct, measured 14 %
+  // slower than the pair on config 2 (profiles/README.md r03f), hence off unless asked for
+  bool use_fused = false;
+  int fused_rc = 0, fused_g = 0, fused_sets = 3, fused_ctas = 0, fused_tpt = 0;   // group shape, scratch ring depth, CTAs per SM (0 = automatic)
   DevBuf d_fsync;                                    // ticket, error flag, per-group counters
   DevBuf d_hint;                                     // per (replica, Doppler) unit: best value reported so far (peak-search floor)
   int v3tab_key[4] = {0, 0, 0, 0};                   // (N, RB, PB, CW) the table was built for
@@ -467,7 +469,7 @@ int correlate_fused(gnssacq* h, const V3Setup& v, int B, int D, int d0, int dc, 
   // replica spectra) inside L2
   job.G = h->fused_g > 0 ? h->fused_g : std::max(1, 4 / B);
   job.G = std::max(1, std::min(job.G, dc));
-  job.Rc = h->fused_rc > 0 ? h->fused_rc : std::max(1, 16 / (job.G * B));
+  job.Rc = h->fused_rc > 0 ? h->fused_rc : std::max(4, 16 / (job.G * B));
   job.Rc = std::max(1, std::min(job.Rc, h->R));
   job.ngr = (h->R + job.Rc - 1) / job.Rc;
   job.ng = job.ngr * ((dc + job.G - 1) / job.G);
@@ -476,7 +478,8 @@ int correlate_fused(gnssacq* h, const V3Setup& v, int B, int D, int d0, int dc, 
   job.nsets = std::max(2, std::min(h->fused_sets, 8));
   job.slots_per_set = job.Rc * job.G * B;
   job.nR = job.nrt * job.Rc;
-  job.nC = job.ntiles * job.Rc * job.G;
+  job.tpt = std::max(1, std::min(h->fused_tpt > 0 ? h->fused_tpt : 5, job.ntiles));
+  job.nC = ((job.ntiles + job.tpt - 1) / job.tpt) * job.Rc * job.G;
   job.D = D; job.d0 = d0; job.n_lags = n_lags; job.zmul = v.F2; job.scale = scale;
   if ((long long)job.ng * (job.nR + job.nC) > 0x7fffffffll) return fail(GNSSACQ_EINVAL, "too many tasks for one fused launch");
   const long long slots = (long long)job.nsets * job.slots_per_set;
@@ -626,6 +629,9 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
 
   int Dc = (int)std::max<size_t>(1, std::min<size_t>((size_t)D, h->xchunk_bytes / (tbytes * B)));
   Dc = std::max(1, std::min(Dc, 65535 / B));
+  // units of a Doppler chunk index grids and 32-bit task counters: keep R * Dc (x tiles) well inside int
+  if ((long long)R * Dc > (1ll << 24)) Dc = (int)std::max<long long>(1, (1ll << 24) / R);
+  if (R > (1 << 24)) return fail(GNSSACQ_EINVAL, "too many replicas for one search");
   if (int rc = h->d_X.ensure((size_t)Dc * B * tbytes)) return rc;
   int Uc = 0;
   if (large && !v3.on) {
@@ -690,9 +696,13 @@ int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned lo
   const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
   const cuuint32_t bx[3] = {box[0], box[1], box[2]};
   const cuuint32_t es[3] = {1, 1, 1};
+  // L2 promotion no wider than a box row: a 64-byte row promoted to 128 bytes drags in the neighbouring
+  // tile's half of the line, which another CTA fetches again later (ncu r03d: 25 B per cell-block
+  // through L2 for 8.5 B of tiles)
+  const CUtensorMapL2promotion promo = box[0] * 8 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : (box[0] * 8 >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), d, st, bx, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 #else
@@ -1050,6 +1060,7 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (std::string(name) == "fused_g") { h->fused_g = value; return 0; }
   if (std::string(name) == "fused_sets") { h->fused_sets = value; return 0; }
   if (std::string(name) == "fused_ctas") { h->fused_ctas = value; return 0; }
+  if (std::string(name) == "fused_tpt") { h->fused_tpt = value; return 0; }
   if (std::string(name) == "v3_rows") { h->v3_rows_variant = value; return 0; }
   if (std::string(name) == "v3_cols") { h->v3_cols_variant = value; return 0; }
   if (std::string(name) == "v3_rc") { h->v3_rc = value; return 0; }

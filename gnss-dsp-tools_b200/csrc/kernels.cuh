@@ -52,7 +52,7 @@ struct FusedJob {
   int R, dc, B;                 // replicas, Doppler bins of this chunk, non-coherent blocks
   int Rc, G;                    // group shape: replicas x Doppler bins
   int ngr, ng;                  // replica groups per Doppler group; number of groups
-  int nrt, ntiles;              // row tiles, column tiles
+  int nrt, ntiles, tpt;         // row tiles, column tiles, column tiles per ticket
   int nsets, slots_per_set;     // scratch ring: sets of Rc*G*B unit-block slots
   int nR, nC;                   // rows / columns tickets per group (fixed; tickets past a ragged edge are empty)
   int D, d0, n_lags, zmul;

@@ -165,11 +165,14 @@ k_corr_fused(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, const int* _
         red_release_add(&sy.rows_done[k], 1);          // ... and published
       }
     } else {
-      // =================================================================== columns task (tile ct, unit ul), B items
+      // =================================================================== columns task: unit ul, tiles ct0 .. ct0+tpt-1, B items each
+      // Several tiles per ticket: the two-slot ring prefetches item i+1 while item i is transformed,
+      // and the ticket / dependency / barrier overhead is paid once per tpt tiles.
       const int nunits_max = job.Rc * job.G;
-      const int ct = idx / nunits_max, ul_full = idx - ct * nunits_max;
+      const int cg = idx / nunits_max, ul_full = idx - cg * nunits_max;
+      const int ct0 = cg * job.tpt, nt = imin(job.tpt, job.ntiles - ct0);
       const int rr = ul_full / job.G, dg = ul_full - rr * job.G;
-      const bool live = rr < ck.Rc && dg < ck.G;
+      const bool live = rr < ck.Rc && dg < ck.G && nt > 0;
       if (tid == 0) {
         if (live && !fused_wait(&sy.rows_done[k], job.nR, sy.error)) s_task[1] = 1; else s_task[1] = 0;
         fence_async_all();                             // the tiles were written through the async proxy and will be read through it
@@ -178,7 +181,9 @@ k_corr_fused(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, const int* _
       const int r = ck.r0 + rr, dd = ck.dd0 + dg;
       const long long unit = (long long)r * job.D + job.d0 + dd;
       const int ul = rr * ck.G + dg;                   // slot numbering of v3_slot
-      auto issue = [&](int b, int slot) {
+      const int nitems = nt * B;
+      auto issue = [&](int item, int slot) {
+        const int ct = ct0 + item / B, b = item % B;
         mbar_arrive_expect(&cfull[slot], (unsigned)(TILE * sizeof(float2)));
         tma_load_3d(smem + slot * SLOT, &map, __ldg(&tile_col0[ct]), 0, (int)((set_base + (long long)ul * B + b) * job.zmul), &cfull[slot]);
       };
@@ -186,33 +191,38 @@ k_corr_fused(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, const int* _
       if (live && s_task[1] == 0) {
         if (tid == 0) { fence_async_smem(); issue(0, 0); }
         const int tc = tid & (CW - 1);
-        const int lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[ct]) + tc]);
-        const float hint = __uint_as_float(__ldcg(&unit_hint[unit]));
         float* qd = DUMP ? q_dump + unit * N : nullptr;
-        float best = -1.f, sum = 0.f;
-        int bestlag = 0x7fffffff;
-        for (int b = 0; b < B; ++b) {
-          const int slot = b & 1;
-          if (b > 0) __syncthreads();                  // everyone is done with the slot the next copy overwrites
-          if (tid == 0 && b + 1 < B) { fence_async_smem(); issue(b + 1, slot ^ 1); }
+        float best = -1.f, sum = 0.f, hint = 0.f;
+        int bestlag = 0x7fffffff, lagc = -1;
+        for (int item = 0; item < nitems; ++item) {
+          const int slot = item & 1, ct = ct0 + item / B, b = item % B;
+          if (item > 0) __syncthreads();               // everyone is done with the slot the next copy overwrites
+          if (tid == 0 && item + 1 < nitems) { fence_async_smem(); issue(item + 1, slot ^ 1); }
+          if (b == 0) {
+            best = -1.f; sum = 0.f; bestlag = 0x7fffffff;
+            lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[ct]) + tc]);
+            hint = __uint_as_float(__ldcg(&unit_hint[unit]));
+          }
           float2* tile = smem + slot * SLOT;
           if (slot == 0) { mbar_wait(&cfull[0], cuse0 & 1u); ++cuse0; } else { mbar_wait(&cfull[1], cuse1 & 1u); ++cuse1; }
           cols_v3_first<SC, CW, THREADS>(tile);
           __syncthreads();
           if (lagc >= 0)
             cols_v3_last<SC, MULTI, DUMP, CW, THREADS>(tile, qs, pl, lagc, b, b + 1 == B, job.n_lags, job.scale, qd, hint, best, bestlag, sum);
-        }
-        unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
-        float sm = sum * job.scale;
-        block_reduce_part(key, sm);
-        if (tid == 0) {
-          Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
-          if (key != 0ull) {
-            const unsigned vb = (unsigned)(key >> 32);
-            p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * job.scale) << 32) | (key & 0xffffffffull);
-            atomicMax(&unit_hint[unit], vb);
+          if (b + 1 == B) {
+            unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
+            float sm = sum * job.scale;
+            block_reduce_part(key, sm);
+            if (tid == 0) {
+              Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
+              if (key != 0ull) {
+                const unsigned vb = (unsigned)(key >> 32);
+                p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * job.scale) << 32) | (key & 0xffffffffull);
+                atomicMax(&unit_hint[unit], vb);
+              }
+              parts[unit * job.ntiles + ct] = p;
+            }
           }
-          parts[unit * job.ntiles + ct] = p;
         }
       }
       if (tid == 0) {

@@ -73,8 +73,23 @@ def library():
             if not os.path.isfile(LIB_PATH):
                 raise NativeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
                                   '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+            _warn_if_stale()
             _lib = _declare(C.CDLL(LIB_PATH))
     return _lib
+
+
+def _warn_if_stale():
+    """A library older than the CUDA sources next to it is a build that was not redone after an
+    edit: say so (the sources do not travel with every installation, so this is only a warning)."""
+    csrc = os.path.join(os.path.dirname(_HERE), 'csrc')
+    if not os.path.isdir(csrc):
+        return
+    built = os.path.getmtime(LIB_PATH)
+    newer = [f for f in os.listdir(csrc) if os.path.getmtime(os.path.join(csrc, f)) > built + 1.0]
+    if newer:
+        import warnings
+        warnings.warn('%s is older than %s: rebuild with `python __graft_entry__.py`' % (LIB_PATH, ', '.join(sorted(newer)[:3])),
+                      RuntimeWarning, stacklevel=3)
 
 
 def _ptr(a):

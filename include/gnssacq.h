@@ -43,6 +43,15 @@ typedef struct {
 
 const char* gnssacq_last_error(void);
 
+/* Host buffers and asynchrony. Calls that take host INPUT pointers (gnssacq_set_signal,
+ * gnssacq_set_replicas[_i8], gnssacq_set_replicas_from_chips, gnssacq_preprocess, the nco_freq list
+ * of the search calls) enqueue their host-to-device copies on the handle's stream and may return
+ * before the copy has run. Pageable memory is staged by CUDA before the call returns, so ordinary
+ * malloc'd / numpy buffers may be reused at once; PINNED (page-locked) buffers are read by DMA
+ * later and must stay valid and unmodified until gnssacq_synchronize() or the next call that
+ * returns results to the host (gnssacq_search, gnssacq_search_grouped, gnssacq_search_sharded,
+ * gnssacq_mix, gnssacq_correlate_bank), all of which synchronise the stream. */
+
 /* Replaces the mp.Pool set-up of acquire-gps-l1.py:105-108: one engine per GPU. */
 int gnssacq_create(int device, gnssacq_t** out);
 int gnssacq_destroy(gnssacq_t* h);

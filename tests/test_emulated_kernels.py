@@ -194,7 +194,7 @@ def test_large_163680_coprime_split_341x480(eng):
     """BASELINE config 2's transform as a coprime (Good-Thomas) four-step: 163680 = 341 x 480, no
     twiddle pass; 341 = 31*11 and 480 = 15*32 are themselves twiddle-free two-stage schedules."""
     info = _case(eng, 163680, False, False, True, 1, (-250, 250, 250), 16.368e6, nprn=1, lag_limit=16368)
-    assert info['N1'] == 341 and info['N2'] == 480 and eng.kernel_variant() == 123 + 256    # 64: copy-engine-fed task bodies, 256: fused persistent kernel
+    assert info['N1'] == 341 and info['N2'] == 480 and eng.kernel_variant() == 123      # 64: copy-engine-fed pair
 
 
 @pytest.mark.slow
@@ -213,7 +213,7 @@ def test_large_163680_register_loading_kernels_on_the_coprime_split(eng):
 def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
     """Every instantiated tile shape of the copy-engine-fed pair, with chunk shapes that leave ragged
     edges (3 replicas in chunks of rc, 5 Doppler bins in groups of g)."""
-    for k, v in (('fused', 0), ('v3_rows', rows), ('v3_cols', cols), ('v3_rc', rc), ('v3_g', g)):
+    for k, v in (('v3_rows', rows), ('v3_cols', cols), ('v3_rc', rc), ('v3_g', g)):
         eng.set_option(k, v)
     try:
         _case(eng, 163680, False, False, True, 1, (-500, 750, 250), 16.368e6, nprn=3, lag_limit=16368)
@@ -221,15 +221,14 @@ def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
     finally:
         for k in ('v3_rows', 'v3_cols', 'v3_rc', 'v3_g'):
             eng.set_option(k, 0)
-        eng.set_option('fused', 1)
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rc,g,sets', [(2, 2, 2), (1, 3, 3), (3, 4, 2)])
-def test_fused_kernel_group_shapes_163680(eng, rc, g, sets):
+@pytest.mark.parametrize('rc,g,sets,tpt', [(2, 2, 2, 1), (1, 3, 3, 7), (3, 4, 2, 60)])
+def test_fused_kernel_group_shapes_163680(eng, rc, g, sets, tpt):
     """The fused persistent kernel with group shapes that leave ragged edges (3 replicas, 5 bins)
     and with the shortest scratch ring (every rows group waits for the columns tasks two groups back)."""
-    for k, v in (('fused_rc', rc), ('fused_g', g), ('fused_sets', sets)):
+    for k, v in (('fused', 1), ('fused_rc', rc), ('fused_g', g), ('fused_sets', sets), ('fused_tpt', tpt)):
         eng.set_option(k, v)
     try:
         _case(eng, 163680, False, False, True, 1, (-500, 750, 250), 16.368e6, nprn=3, lag_limit=16368)
@@ -238,6 +237,8 @@ def test_fused_kernel_group_shapes_163680(eng, rc, g, sets):
         eng.set_option('fused_rc', 0)
         eng.set_option('fused_g', 0)
         eng.set_option('fused_sets', 3)
+        eng.set_option('fused_tpt', 0)
+        eng.set_option('fused', 0)
 
 
 @pytest.mark.slow
@@ -255,7 +256,7 @@ def test_v3_non_coherent_blocks_61380(eng, rows, cols, blocks):
     finally:
         eng.set_option('v3_rows', 0)
         eng.set_option('v3_cols', 0)
-        eng.set_option('fused', 1)
+        eng.set_option('fused', 0)
 
 
 @pytest.mark.slow

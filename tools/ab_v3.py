@@ -71,15 +71,14 @@ for name, n, pad, R, D, B, norm in CASES:
         got = run(name, n, pad, R, D, B, norm, dict(base, v3=1, v3_rows=rv, v3_cols=cv))
         if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
             print('   !! lags differ from the register-loading kernels')
-    # the fused persistent kernel: group shapes, ring depth, CTAs per SM
-    fshapes = [(0, 0), (4, 4), (2, 4), (8, 2), (4, 2), (8, 4), (16, 1)] if B == 1 else [(0, 0), (1, 1), (2, 1), (4, 1)]
-    for (rc, g), sets, ctas in itertools.product(fshapes, (2, 3, 4), (0,)):
-        got = run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=rc, fused_g=g, fused_sets=sets, fused_ctas=ctas))
+    # the fused persistent kernel: group shapes, column tiles per ticket, ring depth
+    fshapes = [(4, 4), (2, 8), (4, 8), (8, 4), (16, 2)] if B == 1 else [(4, 1), (8, 1), (16, 1)]
+    for (rc, g), tpt, sets in itertools.product(fshapes, (1, 3, 5, 10, 15), (3,)):
+        got = run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=rc, fused_g=g, fused_sets=sets, fused_tpt=tpt))
         if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
             print('   !! lags differ from the register-loading kernels')
-    for ctas in (2, 3, 5):
-        run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=0, fused_g=0, fused_sets=3, fused_ctas=ctas))
-    run(name, n, pad, R, D, B, norm, dict(v3=1, fused=0, fused_rc=0, fused_g=0, fused_sets=3, fused_ctas=0))
+    run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=4, fused_g=8, fused_sets=4, fused_tpt=5))
+    run(name, n, pad, R, D, B, norm, dict(v3=1, fused=0, fused_rc=0, fused_g=0, fused_sets=3, fused_tpt=0))
     if quick:
         continue
     # chunk shapes and lanes at the default tiles
