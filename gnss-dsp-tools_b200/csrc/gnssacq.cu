@@ -696,13 +696,12 @@ int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned lo
   const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
   const cuuint32_t bx[3] = {box[0], box[1], box[2]};
   const cuuint32_t es[3] = {1, 1, 1};
-  // L2 promotion no wider than a box row: a 64-byte row promoted to 128 bytes drags in the neighbouring
-  // tile's half of the line, which another CTA fetches again later (ncu r03d: 25 B per cell-block
-  // through L2 for 8.5 B of tiles)
-  const CUtensorMapL2promotion promo = box[0] * 8 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                       : (box[0] * 8 >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
+  // L2 promotion 128 B even for 64-byte box rows: the other half of the line belongs to the neighbouring
+  // column tile, which (tile-major tasks) another CTA fetches shortly after — measured 5 % faster than
+  // 64 B promotion although lts__t_bytes is 30 % higher (profiles/README.md r03g)
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), d, st, bx, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 #else
