@@ -223,6 +223,51 @@ def bench_strong(eng, torch, dist, stream, dev, rank, world, reps=3):
             'tail': 'per-rank forward FFTs of its own bins only; replica set-up outside the timed region; one 16-byte-per-replica all-gather (latency-bound) after the last kernel'}
 
 
+def bench_sweep(eng, torch, dist, dev, rank, world):
+    """BASELINE config 5: the reference's acquire-all.sh job list (21 signal jobs, script-default PRN
+    sets and Doppler grids, 80 ms) on three 50 Msps band recordings, jobs sharded over the ranks by
+    estimated cost (gnsstools/sweep.py; ranks are independent, no collective). Wall clock of the
+    second (warm: code tables built, plans cached) pass, max over ranks; includes reading the files,
+    the GPU front end and writing the acq-*.dat result files."""
+    import tempfile
+    from gnsstools import sweep
+    fs, ms = 50000000.0, 80
+    n = int(fs * 0.001 * (ms + 5))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, 'band.iq')
+        rng = np.random.default_rng(5)
+        rng.integers(-20, 21, 2 * n, dtype=np.int8).tofile(path)          # noise-only recording, the same for the three bands
+        files = {1: path, 2: path, 3: path}
+        times = []
+        for _ in range(2):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = sweep.run(files, fs, os.path.join(tmp, 'out%d' % rank), ms=ms, engine=eng, rank=rank, world=world)
+            eng.synchronize()
+            times.append(time.perf_counter() - t0)
+        t = torch.tensor([times[1]], dtype=torch.float64, device=dev)
+        nj = torch.tensor([len(out)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            njs = [torch.zeros_like(nj) for _ in range(world)]
+            dist.all_gather(njs, nj)
+            per_rank = [int(v.item()) for v in njs]
+        else:
+            per_rank = [len(out)]
+    cells = sum(len(sweep.default_keys(acquire_signals()[j[1]])) * len(np.arange(*[float(v) for v in acquire_signals()[j[1]].doppler.split(',')]))
+                * acquire_signals()[j[1]].N for j in sweep.JOBS)
+    return {'config': 'config5 acquire-all sweep: %d signal jobs, script defaults, 80 ms, 3 x 50 Msps int8 recordings, job-sharded' % len(sweep.JOBS),
+            'n_gpus': world, 'seconds_wall': float(t.item()), 'seconds_first_pass_this_rank': times[0], 'jobs_per_rank': per_rank,
+            'cells': int(cells), 'cells_per_s': cells / float(t.item())}
+
+
+def acquire_signals():
+    from gnsstools import acquire
+    return acquire.SIGNALS
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port: the reference is pure Python
     and cannot travel to the GPU box) on all host cores, same metric/config."""
@@ -383,6 +428,7 @@ def main():
             found += 1
 
     strong = bench_strong(eng, torch, dist, stream, dev, rank, world) if world > 1 and not args.no_extra else None
+    swp = bench_sweep(eng, torch, dist if world > 1 else None, dev, rank, world) if not args.no_extra else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -436,6 +482,8 @@ def main():
         line['configs'] = [bench_shape(eng, torch, stream, dev, cfg, peak) for cfg in EXTRA_CONFIGS]
     if strong is not None:
         line['strong'] = strong
+    if swp is not None:
+        line['sweep'] = swp
     if not args.no_cpu_baseline:
         v, dt, info = cpu_baseline(x.astype(np.complex128), list(range(1, 33)), bins[:D_PER_GPU])
         line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': info['cores'], 'kind': 'port', 'sample': info['sample']}

@@ -27,6 +27,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// plain arrival (no copy traffic announced)
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier over `count` threads of the CTA (a multiple of 32), id 1..15 (0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -70,6 +76,9 @@ bool emu_mbar_test(unsigned long long* bar, unsigned parity);
 inline void mbar_init(unsigned long long* bar, int count) { emu_mbar_init(bar, count); }
 inline void mbar_fence_init() {}
 inline void mbar_arrive_expect(unsigned long long* bar, unsigned bytes) { emu_mbar_arrive(bar, bytes); }
+inline void mbar_arrive(unsigned long long* bar) { emu_mbar_arrive(bar, 0); }
+void emu_named_barrier(int id, int count);
+inline void named_bar_sync(int id, int count) { emu_named_barrier(id, count); }
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { while (!emu_mbar_test(bar, parity)) std::this_thread::yield(); }
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { memcpy(dst, src, bytes); emu_mbar_complete_tx(bar, bytes); }
 inline void bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }

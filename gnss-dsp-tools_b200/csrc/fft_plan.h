@@ -85,6 +85,7 @@ inline int measured_gt_n1(int N) {
   switch (N) {
     case 163680: return 341;         // 341 = 31*11, 480 = 15*32
     case 61380: return 279;          // 279 = 31*9, 220 = 11*20
+    case 30690: return 341;          // 341 = 31*11, 90 = 9*10
     default: return 0;
   }
 }

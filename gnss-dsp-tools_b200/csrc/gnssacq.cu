@@ -1041,6 +1041,46 @@ int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, doubl
   return 0;
 }
 
+int gnssacq_correlate_epl(gnssacq_t* h, const float* x_c64, int32_t nx, int32_t n, const int8_t* chips01, int32_t ncodes, int32_t L,
+                          int32_t mode, const double* params, int32_t H, const int32_t* xsel, const int32_t* csel,
+                          const double* start, const double* incr, double* out_c128) {
+  if (!h || !x_c64 || !chips01 || !xsel || !csel || !start || !incr || !out_c128 || nx <= 0 || n <= 0 || ncodes <= 0 || L <= 0 || H <= 0)
+    return fail(GNSSACQ_EINVAL, "bad correlator arguments");
+  if (mode < 0 || mode > 3 || (mode >= 1 && !params)) return fail(GNSSACQ_EINVAL, "mode must be 0..3 (modes 1-3 need params)");
+  for (int i = 0; i < H; ++i)
+    if (xsel[i] < 0 || xsel[i] >= nx || csel[i] < 0 || csel[i] >= ncodes || !(incr[i] > 0.0)) return fail(GNSSACQ_EINVAL, "hypothesis out of range");
+  CU(cudaSetDevice(h->device));
+  const size_t xb = (size_t)nx * n * sizeof(float2), cb = (size_t)ncodes * L, pb = 37 * sizeof(double);
+  const size_t hb_i = (size_t)H * sizeof(int), hb_d = (size_t)H * sizeof(double);
+  if (int rc = h->d_tmp.ensure(xb)) return rc;
+  if (int rc = h->d_chips.ensure(cb)) return rc;
+  if (int rc = h->d_base.ensure(pb + 2 * hb_d + 2 * hb_i)) return rc;
+  if (int rc = h->d_bank.ensure((size_t)H * sizeof(double2))) return rc;
+  unsigned char* base = h->d_base.as<unsigned char>();
+  double* d_params = reinterpret_cast<double*>(base);
+  double* d_start = d_params + 37;
+  double* d_incr = d_start + H;
+  int* d_xsel = reinterpret_cast<int*>(d_incr + H);
+  int* d_csel = d_xsel + H;
+  double hp[37] = {1.0, 1.0, 0.0, 0.0};
+  if (params) memcpy(hp, params, (mode == 3 ? 37 : 4) * sizeof(double));
+  CU(cudaMemcpyAsync(h->d_tmp.p, x_c64, xb, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_chips.p, chips01, cb, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_params, hp, pb, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_start, start, hb_d, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_incr, incr, hb_d, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_xsel, xsel, hb_i, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_csel, csel, hb_i, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));                    // hp is a local
+  GNSSACQ_LAUNCH(k_correlate_epl, dim3(H), dim3(kThreads), 0, h->stream, h->d_tmp.as<float2>(), n, h->d_chips.as<signed char>(), L, mode,
+                 d_params, d_xsel, d_csel, d_start, d_incr, h->d_bank.as<double2>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_c128, h->d_bank.p, (size_t)H * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (!h || !name) return fail(GNSSACQ_EINVAL, "NULL argument");
   if (std::string(name) == "specialized_kernels") {     // changes the spectrum layout: replicas must be set again

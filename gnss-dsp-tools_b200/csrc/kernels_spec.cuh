@@ -613,6 +613,7 @@ using S248 = Sub<248, 31, 8>;
 using S496 = Sub<496, 31, 16>;
 using S341 = Sub<341, 31, 11>;           // coprime split of 163680 = 341 x 480
 using S480 = Sub<480, 15, 32>;
+using S90 = Sub<90, 9, 10>;              // coprime split of 30690 = 341 x 90
 
 template <class S> inline bool schedule_matches(const SubPlan& sp) {
   if (sp.F != S::F || sp.ns != S::NS || (sp.pfa != 0) != S::kPfa) return false;

@@ -140,6 +140,92 @@ k_corr_rows_v3(DevPlan pl, const float2* __restrict__ X, const float2* __restric
   if (tid == 0) bulk_wait_all<0>();                            // shared memory must outlive the last store
 }
 
+// =========================================================================== rows kernel, balanced
+// Stage B needs T*RA threads — half of the CTA for 480 = 15 * 32 — so in k_corr_rows_v3 half of the warps
+// sit at the block barrier while the others run the radix-32 butterflies (ncu r03d: 35 % of the stall
+// samples are barrier waits). Here the two halves of the CTA take turns: pair (it mod 2) runs stage B of
+// (Doppler, block) pair `it` while the other half already multiplies and transforms pair it+1 into the
+// second exchange buffer. Block barriers become mbarriers:
+//   xfull[s]  spectra tile of ring slot s landed (copy-engine transaction count)
+//   efull[e]  every thread has written its stage-A outputs into exchange buffer e (count THREADS)
+//   efree[e]  the bulk store that read exchange buffer e has drained it (arrived by the half that issued it)
+// Over two pairs every warp does A, A, B. Same arithmetic as k_corr_rows_v3: bit-identical scratch.
+template <class S, int T> __host__ __device__ constexpr size_t rows_v4_smem() {
+  return 2 * (size_t)T * S::F * sizeof(float2) + 2 * (size_t)T * S::radix(0) * v3_pitch(S::radix(1)) * sizeof(float2) + 6 * 8;
+}
+template <class S, int T, int THREADS, int MINCTAS>
+__global__ void __launch_bounds__(THREADS, MINCTAS)
+k_corr_rows_v4(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C, ChunkV3 ck, int B,
+               float2* __restrict__ scratch) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2 && S::kPfa, "two coprime stages");
+  constexpr int N2 = S::F, RA = S::radix(0), RB = S::radix(1), PB = v3_pitch(RB), NP = RA * PB;
+  constexpr int GT = (T * RA + 31) / 32 * 32;                 // threads of one stage-B half
+  static_assert(RB % 2 == 0 && THREADS >= T * RB && THREADS == 2 * GT, "two halves, each large enough for stage B");
+  constexpr int XT = T * N2, ET = T * NP;
+  float2* xbuf = smem;
+  float2* ebuf = smem + 2 * XT;
+  unsigned long long* xfull = reinterpret_cast<unsigned long long*>(ebuf + 2 * ET);
+  unsigned long long* efull = xfull + 2;
+  unsigned long long* efree = xfull + 4;
+  const int N = pl.N, N1 = pl.N1;
+  const int row0 = blockIdx.x * T;
+  const int nrows = imin(T, N1 - row0);
+  const int r = ck.r0 + blockIdx.y;
+  const int nall = ck.G * B, per = (nall + gridDim.z - 1) / gridDim.z;
+  const int it0 = blockIdx.z * per, nit = imin(per, nall - it0);
+  const int tid = threadIdx.x, half = tid / GT, htid = tid - half * GT;
+  const bool leader = htid == 0;
+  const unsigned xbytes = (unsigned)nrows * N2 * sizeof(float2), ebytes = (unsigned)nrows * NP * sizeof(float2);
+
+  auto issue = [&](int it) {                                   // spectra tile of pair `it` -> ring slot it & 1
+    const int g = it0 + it;
+    const float2* src = X + ((long long)(ck.dd0 + g / B) * B + g % B) * N + (long long)row0 * N2;
+    mbar_arrive_expect(&xfull[it & 1], xbytes);
+    bulk_g2s(xbuf + (it & 1) * XT, src, xbytes, &xfull[it & 1]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&xfull[s], 1); mbar_init(&efull[s], THREADS); mbar_init(&efree[s], 1); }
+    mbar_fence_init();
+    for (int it = 0; it < 2 && it < nit; ++it) issue(it);
+  }
+  const int ra = tid / RB, b = tid - ra * RB;
+  const bool act_a = tid < T * RB && ra < nrows;
+  float2 c[RA];
+  if (act_a) {
+    const float2* cp = C + (long long)r * N + (long long)(row0 + ra) * N2 + b;
+#pragma unroll
+    for (int a = 0; a < RA; ++a) c[a] = __ldg(&cp[a * RB]);
+  }
+  __syncthreads();                                             // barrier initialisation visible to every thread
+
+  for (int it = 0; it < nit; ++it) {
+    const int e = it & 1;
+    const unsigned ph = (unsigned)(it >> 1) & 1u;
+    float2* et = ebuf + e * ET;
+    mbar_wait(&xfull[e], ph);
+    if (it >= 2) mbar_wait(&efree[e], ph ^ 1u);                // the store of pair it-2 has drained this buffer
+    if (act_a) rows_v3_stage_a<S>(xbuf + e * XT, et, c, ra, b);
+    mbar_arrive(&efull[e]);
+    if (half == e) {
+      mbar_wait(&efull[e], ph);                                // exchange buffer complete, ring slot e drained
+      if (leader && it + 2 < nit) { fence_async_smem(); issue(it + 2); }
+      if (htid < nrows * RA) { rows_v3_stage_b<S>(et, htid); fence_async_smem(); }
+      named_bar_sync(1 + half, GT);
+      if (leader) {
+        const int g = it0 + it;
+        const int slot = v3_slot(ck, B, r, ck.dd0 + g / B, g % B);
+        bulk_s2g(scratch + ((long long)slot * N1 + row0) * NP, et, ebytes);
+        bulk_commit();
+      }
+    } else if (leader && it >= 1) {
+      bulk_wait_read<0>();                                     // my store of pair it-1 (issued one stage A ago) has read its buffer
+      mbar_arrive(&efree[half]);
+    }
+  }
+  if (leader) bulk_wait_all<0>();                              // shared memory must outlive the last stores
+}
+
 // =========================================================================== cols kernel
 // ring slots start on 128-byte boundaries (tensor-map copies need it)
 template <class S, int CW> __host__ __device__ constexpr int cols_v3_slot() { return (S::F * CW + 15) / 16 * 16; }   // float2 per slot

@@ -29,7 +29,7 @@ fwd_cols_fn find_fwd_cols_kernel(const SubPlan& s1, int src) {
 }
 fwd_rows_fn find_fwd_rows_kernel(const SubPlan& s2) {
 #define TRY(S) if (schedule_matches<S>(s2)) return k_fwd_rows_s<S>;
-  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220) TRY(S480)
+  TRY(S128) TRY(S256) TRY(S512) TRY(S320) TRY(S186) TRY(S279) TRY(S440) TRY(S250) TRY(S165) TRY(S220) TRY(S480) TRY(S90)
 #undef TRY
   return nullptr;
 }
@@ -48,7 +48,7 @@ ColsSmall find_cols_small(const SubPlan& s1, bool multi) {
 corr_rows_fn find_rows_kernel(const SubPlan& s2, bool gt) {
   if (gt) {                              // coprime splits (no four-step twiddle): the lengths that have one
 #define TRY(S) if (schedule_matches<S>(s2)) return k_corr_rows_s<S, true>;
-    TRY(S220) TRY(S480)
+    TRY(S220) TRY(S480) TRY(S90)
 #undef TRY
     return nullptr;
   }
@@ -64,7 +64,7 @@ RowsSmall find_rows_small(const SubPlan& s2, bool gt) {
   static_assert(kRowsSmallTile == kRowsTile8, "row tile");
   if (gt) {
 #define TRY(S, T, C) if (schedule_matches<S>(s2)) return RowsSmall{k_corr_rows_t<S, T, C, true>, T, rows_t_smem<S>()};
-    TRY(S220, 128, 4) TRY(S480, 128, 4)
+    TRY(S220, 128, 4) TRY(S480, 128, 4) TRY(S90, 128, 6)
 #undef TRY
     return RowsSmall{nullptr, 0, 0};
   }
@@ -108,7 +108,11 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
     return RowsV3{k_corr_rows_v3<S, T, TH, C, XB>, TH, T, C, rows_v3_smem<S, T, XB>(), S::radix(0), S::radix(1), v3_pitch(S::radix(1))};
   TRY(S480, 0, 4, 128, 4, 1) TRY(S480, 1, 8, 256, 1, 2) TRY(S480, 2, 8, 256, 2, 1) TRY(S480, 3, 4, 128, 3, 2)
   TRY(S220, 0, 8, 160, 3, 2) TRY(S220, 1, 8, 160, 4, 1)
+  TRY(S90, 0, 8, 96, 8, 1) TRY(S90, 1, 8, 96, 6, 2)
 #undef TRY
+  // balanced kernel (the two halves of the CTA alternate on stage B): 4 warps, stage B = 2 warps
+  if (variant == 4 && schedule_matches<S480>(s2))
+    return RowsV3{k_corr_rows_v4<S480, 4, 128, 3>, 128, 4, 3, rows_v4_smem<S480, 4>(), S480::radix(0), S480::radix(1), v3_pitch(S480::radix(1))};
   return RowsV3{nullptr, 0, 0, 0, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 9

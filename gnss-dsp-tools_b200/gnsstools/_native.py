@@ -52,6 +52,7 @@ def _declare(lib):
         'gnssacq_preprocess': [p, p, i64, dbl, dbl, p, i32, dbl, i64, p],
         'gnssacq_set_replicas_from_chips': [p, p, i32, i32, i32, i32, dbl, dbl, i32, dbl],
         'gnssacq_correlate_bank': [p, p, i32, dbl, i32, i32, i32, p, i32, dbl, p],
+        'gnssacq_correlate_epl': [p, p, i32, i32, p, i32, i32, i32, p, i32, p, p, p, p, p],
         'gnssacq_plan_info': [p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         'gnssacq_synchronize': [p],
         'gnssacq_kernel_variant': [p],
@@ -181,6 +182,26 @@ class Engine:
         out = np.empty(base.shape, dtype=np.complex128)
         self._check(self._lib.gnssacq_correlate_bank(self._h, _ptr(c), c.size, float(nco_freq), int(n), int(n_blocks),
                                                      int(block_stride), _ptr(base), base.shape[0], float(incr), _ptr(out)))
+        return out
+
+    def correlate_epl(self, x, chips01, start, incr, xsel=None, csel=None, mode=0, params=None):
+        """Batched tracking correlators: out[h] = <sig>.correlate(x[xsel[h]], ., start[h], 0, incr[h], chips01[csel[h]], ...)
+        of the reference (mode 0 plain, 1 two-level sub-chip pattern, 2 CBOC, 3 TMBOC; see gnssacq.h).
+        x: (nx, n) or (n,) complex64 blocks, chips01: (ncodes, L) or (L,) 0/1 chips."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.complex64)
+        c = np.ascontiguousarray(np.atleast_2d(chips01), dtype=np.int8)
+        start = np.ascontiguousarray(np.atleast_1d(start), dtype=np.float64)
+        H = start.size
+        incr = np.ascontiguousarray(np.broadcast_to(np.asarray(incr, dtype=np.float64), (H,)))
+        xsel = np.zeros(H, np.int32) if xsel is None else np.ascontiguousarray(xsel, dtype=np.int32)
+        csel = np.zeros(H, np.int32) if csel is None else np.ascontiguousarray(csel, dtype=np.int32)
+        prm = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        if prm is not None and prm.size < (37 if mode == 3 else 4):
+            raise ValueError('params: {sub0, sub1, a1, a6[, pattern x 33]}')
+        out = np.empty(H, np.complex128)
+        self._check(self._lib.gnssacq_correlate_epl(self._h, _ptr(x), x.shape[0], x.shape[1], _ptr(c), c.shape[0], c.shape[1], int(mode),
+                                                    _ptr(prm) if prm is not None else None, H, _ptr(xsel), _ptr(csel), _ptr(start), _ptr(incr),
+                                                    _ptr(out)))
         return out
 
     def set_replicas_i8_device(self, device_ptr, R, N):

@@ -174,6 +174,25 @@ int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, doubl
                            int32_t n_blocks, int32_t block_stride, const double* base, int32_t H, double incr,
                            double* out_c128);
 
+/* Batched tracking correlators (second half): `<sig>.correlate(x, prn, chips,
+ * frac, incr, c[, boc11])` of the tracking scripts (track-gps-l1.py:51-53: early / prompt / late) for
+ * H hypotheses (channel x tap) in one call:
+ *   out[h] = sum_{i<n} x[xsel[h]*n + i] * (1 - 2*chips01[csel[h]*L + int(cp_i)]) * sub_i
+ *   cp_0 = start[h] mod L (start = chips + frac, formed by the caller in float64),
+ *   cp_{i+1} = (cp_i + incr[h]) mod L — the reference's float64 recurrence, evaluated as such, so every
+ *   sample sees the chip the reference's loop sees.
+ * mode 0: sub_i = 1                                      gnsstools/gps/ca.py:120-128
+ * mode 1: sub_i = sub[int(bp_i)], bp_0 = (2*start) mod 2, bp += 2*incr (mod 2)   BOC(1,1) / L2C RZ slots
+ * mode 2: sub_i = a1*sub[int(bp_i)] + a6*sub[int(bp6_i)], bp6_0 = (12*start) mod 2, bp6 += 12*incr   gnsstools/galileo/e1b.py:45-58
+ * mode 3: sub_i = pattern[int(cp_i) mod 33] ? sub[int(bp6_i)] : sub[int(bp_i)]          gnsstools/gps/l1cp.py:210-228
+ * params (modes 1-3): {sub[0], sub[1], a1, a6, pattern[0..32]} (37 doubles for mode 3, 4 otherwise).
+ * x_c64: nx blocks of n complex64 samples (already carrier-wiped, as track() does with nco.mix);
+ * chips01: ncodes tables of L chips; out_c128: H complex128, interleaved re,im. Data-parallel across
+ * hypotheses, sequential in time inside each (one CTA per hypothesis). */
+int gnssacq_correlate_epl(gnssacq_t* h, const float* x_c64, int32_t nx, int32_t n, const int8_t* chips01, int32_t ncodes, int32_t L,
+                          int32_t mode, const double* params, int32_t H, const int32_t* xsel, const int32_t* csel,
+                          const double* start, const double* incr, double* out_c128);
+
 int gnssacq_plan_info(gnssacq_t* h, int32_t* N, int32_t* N1, int32_t* N2, int32_t* large);
 int64_t gnssacq_launch_count(gnssacq_t* h);   /* kernels launched by this handle so far */
 /* Which correlate kernels the current plan runs: bit 0 = specialised rows kernel, bit 1 =

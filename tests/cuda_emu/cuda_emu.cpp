@@ -128,6 +128,22 @@ void emu_mbar_complete_tx(unsigned long long* bar, long long bytes) {
   s.tx -= bytes;
   mbar_settle(s);
 }
+// bar.sync id, count: `count` threads of the running block meet at barrier `id`
+void emu_named_barrier(int id, int count) {
+  static std::mutex mu;
+  static int arrived[16] = {0};
+  static long gen[16] = {0};
+  long my;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    my = gen[id & 15];
+    if (++arrived[id & 15] == count) { arrived[id & 15] = 0; ++gen[id & 15]; return; }
+  }
+  for (;;) {
+    { std::lock_guard<std::mutex> g(mu); if (gen[id & 15] != my) return; }
+    std::this_thread::yield();
+  }
+}
 bool emu_mbar_test(unsigned long long* bar, unsigned parity) {
   std::lock_guard<std::mutex> g(mbar_mu);
   return mbar_tab.at(bar).phase != (parity & 1u);

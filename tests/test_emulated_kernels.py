@@ -209,7 +209,7 @@ def test_large_163680_register_loading_kernels_on_the_coprime_split(eng):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4)])
+@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4), (4, 0, 2, 5), (4, 1, 3, 1)])
 def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
     """Every instantiated tile shape of the copy-engine-fed pair, with chunk shapes that leave ragged
     edges (3 replicas in chunks of rc, 5 Doppler bins in groups of g)."""
@@ -309,3 +309,18 @@ def test_grouped_search_equals_one_search_per_group(eng):
         assert np.array_equal(m, M[g]) and np.array_equal(l, L[g]) and np.array_equal(d, Dd[g])
     with pytest.raises(ValueError):
         eng.search_grouped(np.zeros(7), 3, n, 2, True)          # not a whole number of groups
+
+
+@pytest.mark.slow
+def test_30690_coprime_split_341x90_with_ragged_column_tiles(eng):
+    """30690 = 341 x 90 (E6, Xona X5): 90 = 9 * 10 has rows of 10-element groups, which 8-column tiles do not
+    divide — the columns kernel walks the flat padded row and masks what lies behind it."""
+    info = _case(eng, 15345, True, False, False, 2, (-400, 400, 200), 15.345e6, nprn=2)
+    assert (info['N1'], info['N2']) == (341, 90) and eng.kernel_variant() == 123
+    _case(eng, 30690, False, False, True, 2, (-400, 400, 400), 30.69e6, nprn=1)
+    eng.set_option('v3', 0)
+    try:
+        _case(eng, 15345, True, False, False, 2, (-400, 400, 200), 15.345e6, nprn=2)
+        assert eng.kernel_variant() == 59
+    finally:
+        eng.set_option('v3', 1)
