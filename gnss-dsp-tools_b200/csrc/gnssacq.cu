@@ -615,7 +615,8 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   const DevPlan& p = h->dp;
   const bool large = h->hp.large;
   const V3Setup v3 = large ? v3_setup(h, B > 1, d_qdump != nullptr) : V3Setup();
-  const int ntiles = v3.on ? v3.ntiles : (large ? (p.N2 + kTileW - 1) / kTileW : 1);
+  // parts per (replica, Doppler): one per tile, or per tile and warp (single-slot columns kernel)
+  const int ntiles = v3.on ? v3.ntiles * (v3.f.fn ? 1 : v3.c.parts_per_tile) : (large ? (p.N2 + kTileW - 1) / kTileW : 1);
   const float scale = 1.0f / (float)N;
   const size_t tbytes = (size_t)N * sizeof(float2);
 

@@ -242,14 +242,29 @@ template <class S, bool MULTI, int CW> __host__ __device__ constexpr size_t cols
 // thread, its warp or — through `unit_hint` — any finished tile of the same (replica, Doppler) unit
 // has seen. Any such value is a lower bound of the unit's maximum, so no candidate for the unit's
 // (maximum, lowest lag) is ever skipped; tiles that cannot hold it simply report nothing.
-template <class S, bool MULTI, bool DUMP, int CW, int THREADS>
-__device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, const DevPlan& pl, int lagc, int b, bool last,
-                                            int n_lags, float scale, float* qd, float hint,
-                                            float& best, int& bestlag, float& sum) {
+// Inputs of the radix-R0 butterfly at tile offset i (column tc): x0, the symmetric / antisymmetric
+// pairs a[j] = x[j] + x[R0-j], bq[j] = x[j] - x[R0-j], and output 0 = the plain sum.
+template <class S, int CW>
+__device__ __forceinline__ void cols_v3_inputs(const float2* tile, int i, int tc, float2& x0, float2* a, float2* bq, float2& s0) {
   constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
-  static_assert(R0 % 2 == 1 && R0 >= 7, "prime radix fused with the epilogue");
-  const int tc = threadIdx.x & (CW - 1), tb = threadIdx.x / CW;
-  constexpr int nb = THREADS / CW;
+  const float2* p = tile + i * CW + tc;
+  x0 = p[0];
+  s0 = x0;
+  static_for<1, H + 1>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const float2 u = p[j * m0 * CW], w = p[(R0 - j) * m0 * CW];
+    a[j] = cadd(u, w);
+    bq[j] = csub(u, w);
+    s0 = cadd(s0, a[j]);
+  });
+}
+
+// Outputs of that butterfly, straight into |.|, the non-coherent sum and the peak search.
+template <class S, bool MULTI, bool DUMP, int CW>
+__device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a, const float2* bq, const float2 s0, int i, float* qs, int tc,
+                                               const DevPlan& pl, int lagc, int b, bool last, int n_lags, float scale, float* qd, float hint,
+                                               float& best, int& bestlag, float& sum) {
+  constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
   const int N2 = pl.N2, Nfull = pl.N;
   auto lag_of = [&](int n1i, int q) -> int {
     int n1;
@@ -258,79 +273,81 @@ __device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, cons
     const int l = n1 * N2 + lagc;
     return l >= Nfull ? l - Nfull : l;                          // wraps only for coprime splits
   };
+  float* qp = qs + i * CW + tc;
+  int n1i = i;
+  if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
+  float floor_ = fmaxf(fmaxf(best, hint), 0.f);
+  // NB outputs v[t] with digit qof(t): magnitudes, accumulation over blocks, sum, peak candidates
+  auto sink = [&](auto NBc, auto qof, const float2* v) {
+    constexpr int NB = decltype(NBc)::value;
+    float acc[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(fmaf(v[t].x, v[t].x, v[t].y * v[t].y));
+    if constexpr (MULTI) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        float* q1 = qp + qof(t) * m0 * CW;
+        if (b > 0) acc[t] += *q1;
+        if (!last) *q1 = acc[t];
+      }
+      if (!last) return;
+    }
+    float m = acc[0];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) sum += acc[t];
+#pragma unroll
+    for (int t = 1; t < NB; ++t) m = fmaxf(m, acc[t]);
+    if (m >= floor_) {
+      // rare once the floor is warm. The digit goes through an opaque move so that the lag arithmetic
+      // stays inside the branch (ptxas otherwise hoists ~100 integer instructions per butterfly into
+      // the common path).
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        if (acc[t] >= floor_) {
+          int q = qof(t);
+#if defined(__CUDA_ARCH__)
+          asm volatile("" : "+r"(q));
+#endif
+          const int lag = lag_of(n1i, q);
+          if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; }
+        }
+      }
+      floor_ = fmaxf(floor_, best);
+#if defined(__CUDA_ARCH__)
+      // share the new floor with the lanes that came along (a lower bound of the unit maximum)
+      floor_ = __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(floor_)));
+#endif
+    }
+    if constexpr (DUMP) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) qd[lag_of(n1i, qof(t))] = acc[t] * scale;
+    }
+  };
+  sink(std::integral_constant<int, 1>{}, [](int) { return 0; }, &s0);
+  prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
+    constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
+    float2 v[2 * nk];
+#pragma unroll
+    for (int t = 0; t < nk; ++t) {
+      v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
+      v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
+    }
+    sink(std::integral_constant<int, 2 * nk>{}, [](int t) { return (t & 1) ? R0 - (k0 + t / 2) : k0 + t / 2; }, v);
+  });
+}
+
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS>
+__device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, const DevPlan& pl, int lagc, int b, bool last,
+                                            int n_lags, float scale, float* qd, float hint,
+                                            float& best, int& bestlag, float& sum) {
+  constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
+  static_assert(R0 % 2 == 1 && R0 >= 7, "prime radix fused with the epilogue");
+  const int tc = threadIdx.x & (CW - 1), tb = threadIdx.x / CW;
+  constexpr int nb = THREADS / CW;
   for (int i = tb; i < m0; i += nb) {
-    const float2* p = tile + i * CW + tc;
-    float* qp = qs + i * CW + tc;
-    float2 a[H + 1], bq[H + 1];
-    const float2 x0 = p[0];
-    float2 s0 = x0;
-    static_for<1, H + 1>([&](auto J) {
-      constexpr int j = decltype(J)::value;
-      const float2 u = p[j * m0 * CW], w = p[(R0 - j) * m0 * CW];
-      a[j] = cadd(u, w);
-      bq[j] = csub(u, w);
-      s0 = cadd(s0, a[j]);
-    });
-    int n1i = i;
-    if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
-    float floor_ = fmaxf(fmaxf(best, hint), 0.f);
-    // NB outputs v[t] with digit qof(t): magnitudes, accumulation over blocks, sum, peak candidates
-    auto sink = [&](auto NBc, auto qof, const float2* v) {
-      constexpr int NB = decltype(NBc)::value;
-      float acc[NB];
-#pragma unroll
-      for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(fmaf(v[t].x, v[t].x, v[t].y * v[t].y));
-      if constexpr (MULTI) {
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-          float* q1 = qp + qof(t) * m0 * CW;
-          if (b > 0) acc[t] += *q1;
-          if (!last) *q1 = acc[t];
-        }
-        if (!last) return;
-      }
-      float m = acc[0];
-#pragma unroll
-      for (int t = 0; t < NB; ++t) sum += acc[t];
-#pragma unroll
-      for (int t = 1; t < NB; ++t) m = fmaxf(m, acc[t]);
-      if (m >= floor_) {
-        // rare once the floor is warm. The digit goes through an opaque move so that the lag arithmetic
-        // stays inside the branch (ptxas otherwise hoists ~100 integer instructions per butterfly into
-        // the common path).
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-          if (acc[t] >= floor_) {
-            int q = qof(t);
-#if defined(__CUDA_ARCH__)
-            asm volatile("" : "+r"(q));
-#endif
-            const int lag = lag_of(n1i, q);
-            if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; }
-          }
-        }
-        floor_ = fmaxf(floor_, best);
-#if defined(__CUDA_ARCH__)
-        // share the new floor with the lanes that came along (a lower bound of the unit maximum)
-        floor_ = __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(floor_)));
-#endif
-      }
-      if constexpr (DUMP) {
-#pragma unroll
-        for (int t = 0; t < NB; ++t) qd[lag_of(n1i, qof(t))] = acc[t] * scale;
-      }
-    };
-    sink(std::integral_constant<int, 1>{}, [](int) { return 0; }, &s0);
-    prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
-      constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
-      float2 v[2 * nk];
-#pragma unroll
-      for (int t = 0; t < nk; ++t) {
-        v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
-        v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
-      }
-      sink(std::integral_constant<int, 2 * nk>{}, [](int t) { return (t & 1) ? R0 - (k0 + t / 2) : k0 + t / 2; }, v);
-    });
+    float2 a[H + 1], bq[H + 1], x0, s0;
+    cols_v3_inputs<S, CW>(tile, i, tc, x0, a, bq, s0);
+    cols_v3_outputs<S, MULTI, DUMP, CW>(x0, a, bq, s0, i, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
   }
 }
 
@@ -424,6 +441,90 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
           atomicMax(&unit_hint[unit], vb);
         }
         parts[unit * ntiles + ct] = p;
+      }
+    }
+    task = ntask; b = nblk;
+  }
+}
+
+// =========================================================================== cols kernel, one tile slot
+// The radix-31 stage reads its 31 inputs at once and then computes ~700 instructions from registers, so
+// the tile slot is free long before the tile is finished: the next tensor-map copy is issued right after
+// those reads, into the SAME slot. Half the shared memory of k_corr_cols_v3 (more CTAs per SM) and two
+// block barriers per tile instead of four: the per-tile results are reduced per WARP and written as
+// THREADS/32 parts per tile (k_finalize folds whatever number of parts a unit has).
+template <class S, bool MULTI, int CW> __host__ __device__ constexpr size_t cols_v5_smem() {
+  return (size_t)cols_v3_slot<S, CW>() * sizeof(float2) + (MULTI ? (size_t)S::F * CW * sizeof(float) : 0) + 16;
+}
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS>
+__global__ void __launch_bounds__(THREADS, MINCTAS)
+k_corr_cols_v5(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, const int* __restrict__ tile_col0,
+               ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
+               Part* __restrict__ parts, float* __restrict__ q_dump, unsigned* __restrict__ unit_hint) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2 && (CW == 8 || CW == 16), "two-stage columns schedule, tile width");
+  constexpr int N1 = S::F, TILE = N1 * CW, SLOT = cols_v3_slot<S, CW>(), NW = THREADS / 32;
+  constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
+  static_assert(THREADS / CW >= m0, "one radix-R0 butterfly per thread");
+  float* qs = reinterpret_cast<float*>(smem + SLOT);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v5_smem<S, MULTI, CW>() - 16);
+  const int N = pl.N;
+  const int tid = threadIdx.x, tc = tid & (CW - 1), tb = tid / CW;
+  const int nunits = ck.Rc * ck.G, ntasks = nunits * ntiles;
+  auto issue = [&](int task, int b) {                          // thread 0
+    const int ct = task / nunits, ul = task - ct * nunits;
+    mbar_arrive_expect(full, (unsigned)(TILE * sizeof(float2)));
+    tma_load_3d(smem, &map, __ldg(&tile_col0[ct]), 0, (ul * B + b) * zmul, full);
+  };
+  int task = blockIdx.x, b = 0;
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_fence_init();
+    tma_prefetch_map(&map);
+    if (task < ntasks) issue(task, 0);
+  }
+  __syncthreads();
+  float best = -1.f, sum = 0.f, hint = 0.f;
+  int bestlag = 0x7fffffff, lagc = -1;
+  for (unsigned seq = 0; task < ntasks; ++seq) {
+    int ntask = task, nblk = b + 1;
+    if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
+    const int ct = task / nunits, ul = task - ct * nunits;
+    const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
+    const long long unit = (long long)r * D + d0 + dd;
+    const bool last = (b + 1 == B);
+    if (b == 0) {
+      best = -1.f; sum = 0.f; bestlag = 0x7fffffff;
+      lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[ct]) + tc]);
+      hint = __uint_as_float(__ldcg(&unit_hint[unit]));
+    }
+    float* qd = DUMP ? q_dump + unit * N : nullptr;
+    mbar_wait(full, seq & 1u);
+    cols_v3_first<S, CW, THREADS>(smem);
+    __syncthreads();
+    const bool act = lagc >= 0 && tb < m0;                     // pad columns and spare butterfly slots only keep the barriers
+    float2 a[H + 1], bq[H + 1], x0, s0;
+    if (act) cols_v3_inputs<S, CW>(smem, tb, tc, x0, a, bq, s0);
+    __syncthreads();                                           // every input is in registers: the slot is free
+    if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk); }
+    if (act) cols_v3_outputs<S, MULTI, DUMP, CW>(x0, a, bq, s0, tb, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
+    if (last) {
+      unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
+      float sm = sum * scale;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        key = k2 > key ? k2 : key;
+      }
+      if ((tid & 31) == 0) {
+        Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
+        if (key != 0ull) {
+          const unsigned vb = (unsigned)(key >> 32);
+          p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
+          atomicMax(&unit_hint[unit], vb);
+        }
+        parts[(unit * ntiles + ct) * NW + (tid >> 5)] = p;
       }
     }
     task = ntask; b = nblk;

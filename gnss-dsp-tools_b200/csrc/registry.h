@@ -33,7 +33,7 @@ ColsSmall find_cols_small(const SubPlan& s1, bool multi);
 typedef void (*rows_v3_fn)(DevPlan, const float2*, const float2*, ChunkV3, int, float2*);
 typedef void (*cols_v3_fn)(DevPlan, const TensorMap, int, const int*, ChunkV3, int, int, int, int, float, int, Part*, float*, unsigned*);
 struct RowsV3 { rows_v3_fn fn; int threads, T, ctas_per_sm; size_t smem; int RA, RB, PB; };
-struct ColsV3 { cols_v3_fn fn; int threads, CW, ctas_per_sm; size_t smem; };
+struct ColsV3 { cols_v3_fn fn; int threads, CW, ctas_per_sm; size_t smem; int parts_per_tile; };   // parts per (unit, tile): 1, or one per warp
 RowsV3 find_rows_v3(const SubPlan& s2, int variant);
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant);   // dump: also writes the q grid (tests)
 

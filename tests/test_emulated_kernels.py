@@ -209,7 +209,7 @@ def test_large_163680_register_loading_kernels_on_the_coprime_split(eng):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4), (4, 0, 2, 5), (4, 1, 3, 1)])
+@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4), (4, 0, 2, 5), (4, 1, 3, 1), (0, 3, 2, 2), (0, 4, 3, 5)])
 def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
     """Every instantiated tile shape of the copy-engine-fed pair, with chunk shapes that leave ragged
     edges (3 replicas in chunks of rc, 5 Doppler bins in groups of g)."""
@@ -242,7 +242,7 @@ def test_fused_kernel_group_shapes_163680(eng, rc, g, sets, tpt):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2)])   # 279 x 220: two tile shapes each
+@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2), (0, 3, 3)])   # 279 x 220: tile shapes; 3 = single-slot columns kernel
 def test_v3_non_coherent_blocks_61380(eng, rows, cols, blocks):
     """279 x 220 with several non-coherent blocks: the (Doppler, block) list walked by the rows
     kernel (split over grid.z), q accumulated in shared memory by the columns kernel."""
