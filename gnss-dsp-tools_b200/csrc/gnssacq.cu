@@ -567,8 +567,8 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
           float2* scr = h->d_scratch_lane[k % h->nlanes].as<float2>();
           GNSSACQ_LAUNCH(kr, dim3(nrt, B, uc), dim3(tr), smr, st,
                          p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, scr);
-          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(tcn), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
-                         ntiles, h->d_parts.as<Part>(), d_qdump);
+          GNSSACQ_LAUNCH(kc, dim3(uc, ntiles), dim3(tcn), smc, st, p, scr, R, B, D, d0, u0, n_lags, scale,
+                         ntiles, h->d_parts.as<Part>(), d_qdump, h->d_hint.as<unsigned>());
           nl += 2;
         }
         h->launches += nl;
@@ -586,9 +586,9 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
                            p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
           }
           StageTimer timer(h, kStageCorrCols, 1);
-          GNSSACQ_LAUNCH(kc, dim3(ntiles, uc), dim3(tcn), smc, h->stream, p,
+          GNSSACQ_LAUNCH(kc, dim3(uc, ntiles), dim3(tcn), smc, h->stream, p,
                          h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
-                         h->d_parts.as<Part>(), d_qdump);
+                         h->d_parts.as<Part>(), d_qdump, h->d_hint.as<unsigned>());
           h->launches += 2;
         }
       }
@@ -623,7 +623,7 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
   if (int rc = h->d_freq.ensure((size_t)D * sizeof(double))) return rc;
   CU(cudaMemcpyAsync(h->d_freq.p, nco_freq, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (int rc = h->d_parts.ensure((size_t)R * D * ntiles * sizeof(Part))) return rc;
-  if (v3.on) {
+  if (large) {
     if (int rc = h->d_hint.ensure((size_t)R * D * sizeof(unsigned))) return rc;
     CU(cudaMemsetAsync(h->d_hint.p, 0, (size_t)R * D * sizeof(unsigned), h->stream));
   }

@@ -319,19 +319,20 @@ k_corr_rows(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__
     }
 }
 
-// grid = (ceil(N2/16), units). Inverse column FFT of every block, |.|, non-coherent sum,
+// grid = (units, ceil(N2/16)). Inverse column FFT of every block, |.|, non-coherent sum,
 // per-tile max/argmax/sum. Shared memory: tile[N1][16] float2 (+ q[N1][16] float if B > 1).
 template <int RC>
 __global__ void __launch_bounds__(kThreads, 2)
 k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D, int d0, int u0,
-            int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
+            int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump,
+            unsigned* __restrict__ /*unit_hint: used by the specialised kernels only*/) {
   GNSSACQ_DYN_SMEM(float2, tile);
   const int N = pl.N, N1 = pl.N1, N2 = pl.N2;
   float* qs = reinterpret_cast<float*>(tile + N1 * kTileW);
   const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW, nb = blockDim.x / kTW;
-  const int col0 = blockIdx.x * kTileW;
+  const int col0 = blockIdx.y * kTileW;                    // grid = (units, tiles), as k_corr_cols_s
   const int ncols = imin(kTileW, N2 - col0);
-  const int ul = blockIdx.y, u = u0 + ul;
+  const int ul = blockIdx.x, u = u0 + ul;
   const int r = u % R, dd = u / R;
   unsigned long long key = 0ull;
   float sum = 0.f;
@@ -362,7 +363,7 @@ k_corr_cols(DevPlan pl, const float2* __restrict__ scratch, int R, int B, int D,
   block_reduce_part(key, sum);
   if (threadIdx.x == 0) {
     Part p; p.key = key; p.sum = sum; p.pad = 0.f;
-    parts[((long long)r * D + d0 + dd) * ntiles + blockIdx.x] = p;
+    parts[((long long)r * D + d0 + dd) * ntiles + blockIdx.y] = p;
   }
 }
 

@@ -191,8 +191,10 @@ k_corr_rows_s(DevPlan pl, const float2* __restrict__ X, const float2* __restrict
 }
 
 // =========================================================================== cols kernel
-// grid = (ceil(N2/16), units), as k_corr_cols. S = schedule of the length-N1 transform.
-// MULTI = more than one non-coherent block (q kept in shared memory between blocks).
+// grid = (units, ceil(N2/16)): units fastest, so the tiles of one unit are spread over the waves and
+// all but the first start with a warm peak-search floor (unit_hint, see kernels_v3.cuh).
+// S = schedule of the length-N1 transform. MULTI = more than one non-coherent block (q kept in shared
+// memory between blocks).
 __device__ __forceinline__ float sqrt_fast(float a) {
 #if defined(__CUDA_ARCH__)
   float r;
@@ -216,7 +218,9 @@ __device__ __forceinline__ float sqrt_fast(float a) {
 template <class S, bool MULTI, int THREADS = kThreads, bool SPLIT = true, int TW = kTW>
 __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, const DevPlan& pl, int ncols, int lag0,
                                                 int b, bool last, int n_lags, float scale, float* qd,
-                                                float& best, int& bestlag, float& sum) {
+                                                float& best, int& bestlag, float& sum, float hint = 0.f) {
+  // hint: the best eligible value an earlier tile of the same (replica, Doppler) unit reported (0 if none):
+  // a lower bound of the unit maximum, so candidates below it cannot be the unit's peak (kernels_v3.cuh).
   static_assert(!SPLIT || TW == kTW, "the warp-pair butterfly assumes 16-column tiles");
   constexpr int WP = TW;
   const int N2 = pl.N2;
@@ -264,16 +268,18 @@ __device__ __forceinline__ void cols_last_stage(const float2* tile, float* qs, c
 #pragma unroll
     for (int t = 0; t < NB; ++t) { sum += acc[t]; m = fmaxf(m, acc[t]); }
 #if defined(__CUDA_ARCH__)
-    const float thr = fmaxf(best, __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(fmaxf(best, 0.f)))));
+    const float flo = fmaxf(best, hint);
+    const float thr = fmaxf(flo, __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(fmaxf(flo, 0.f)))));
 #else
-    const float thr = best;
+    const float flo = fmaxf(best, hint);
+    const float thr = flo;
 #endif
     if (m >= thr) {
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
-        if (acc[t] >= best) {
+        if (acc[t] >= flo) {
           const int lag = lag_of(n1_of(n1i, qof(t)));
-          if (lag < n_lags && (acc[t] > best || lag < bestlag)) { best = acc[t]; bestlag = lag; }
+          if (lag < n_lags && (acc[t] > best || (acc[t] == best && lag < bestlag))) { best = acc[t]; bestlag = lag; }
         }
       }
     }
@@ -392,21 +398,25 @@ template <class S> __host__ __device__ constexpr int cols_min_ctas() {
 template <class S, bool MULTI, int THREADS = kThreads, int MINCTAS = cols_min_ctas<S>(), bool SPLIT = true>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int D, int d0, int u0,
-              int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump) {
+              int n_lags, float scale, int ntiles, Part* __restrict__ parts, float* __restrict__ q_dump,
+              unsigned* __restrict__ unit_hint) {
   GNSSACQ_DYN_SMEM(float2, tile);
   constexpr int N1 = S::F, WP = kTileW, NS = S::NS;
   const int N = pl.N, N2 = pl.N2;
   float* qs = reinterpret_cast<float*>(tile + N1 * WP);
   const int tc = threadIdx.x & (kTW - 1), tb = threadIdx.x / kTW;
   constexpr int nb = THREADS / kTW;
-  const int col0 = blockIdx.x * kTileW;
+  const int tileno = blockIdx.y;
+  const int col0 = tileno * kTileW;
   const int ncols = imin(kTileW, N2 - col0);
-  const int ul = blockIdx.y, u = u0 + ul;
+  const int ul = blockIdx.x, u = u0 + ul;
   const int r = u % R_, dd = u / R_;
+  const long long unit = (long long)r * D + d0 + dd;
   // Per-thread running peak over the eligible lags (unscaled; 1/N is applied once at the end).
   float best = -1.f, sum = 0.f;
   int bestlag = 0x7fffffff;
-  float* qd = q_dump ? q_dump + ((long long)r * D + d0 + dd) * N : nullptr;
+  const float hint = unit_hint ? __uint_as_float(__ldcg(&unit_hint[unit])) : 0.f;
+  float* qd = q_dump ? q_dump + unit * N : nullptr;
   const int lag0 = col0 + tc;
 
   for (int b = 0; b < B; ++b) {
@@ -429,15 +439,21 @@ k_corr_cols_s(DevPlan pl, const float2* __restrict__ scratch, int R_, int B, int
       __syncthreads();
     }
     inv_stages_smem<S, NS - 2, 1, WP, 1, THREADS>(tile, ncols, pl.s1);
-    cols_last_stage<S, MULTI, THREADS, SPLIT>(tile, qs, pl, ncols, lag0, b, last, n_lags, scale, qd, best, bestlag, sum);
+    cols_last_stage<S, MULTI, THREADS, SPLIT>(tile, qs, pl, ncols, lag0, b, last, n_lags, scale, qd, best, bestlag, sum, hint);
     if (MULTI && !last) __syncthreads();       // tile and q are reused by the next block
   }
-  unsigned long long key = bestlag != 0x7fffffff ? pack_key(best * scale, bestlag) : 0ull;
+  // reduce on the unscaled value (the hint must be bit-exactly a value that occurred; scaling by 1/N is monotonic)
+  unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
   sum *= scale;
   block_reduce_part(key, sum);
   if (threadIdx.x == 0) {
-    Part p; p.key = key; p.sum = sum; p.pad = 0.f;
-    parts[((long long)r * D + d0 + dd) * ntiles + blockIdx.x] = p;
+    Part p; p.key = 0ull; p.sum = sum; p.pad = 0.f;
+    if (key != 0ull) {
+      const unsigned vb = (unsigned)(key >> 32);
+      p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
+      if (unit_hint) atomicMax(&unit_hint[unit], vb);
+    }
+    parts[unit * ntiles + tileno] = p;
   }
 }
 

@@ -9,7 +9,7 @@
 namespace acq {
 
 typedef void (*corr_rows_fn)(DevPlan, const float2*, const float2*, int, int, int, float2*);
-typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*);
+typedef void (*corr_cols_fn)(DevPlan, const float2*, int, int, int, int, int, int, float, int, Part*, float*, unsigned*);
 typedef void (*fwd_cols_fn)(DevPlan, const float2*, const float*, const double*, const float2*, int, int, float2*);
 typedef void (*fwd_rows_fn)(DevPlan, float2*);
 

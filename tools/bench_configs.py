@@ -17,6 +17,7 @@ CASES = [
     ('config1 gps-l1 PRN1 1ms', 4096, False, 1, 20, 1, True),
     ('gps-l1 defaults 32PRN 70D 80blk', 4096, False, 32, 70, 80, True),
     ('glonass-l1 1chan 70D 80blk', 16384, False, 1, 70, 80, False),
+    ('glonass-l1 defaults 15chan x 70D 80blk, one grouped call', 16384, False, 1, 15 * 70, 80, False),
     ('b1i 63PRN 70D 80blk', 8192, True, 63, 70, 80, False),
     ('config3 e1b+e1c ref-style 65536', 32768, True, 72, 360, 1, False),
     ('e1b defaults 50PRN 360D 19blk', 32768, True, 50, 360, 19, False),
@@ -54,7 +55,10 @@ for name, n, pad, R, D, B, norm in CASES:
     eng.set_replicas(rep)
     rec = torch.zeros(4 * R, dtype=torch.int32, device=dev)
     def step():
-        eng.search_device(f, n, B, norm, 0, rec.data_ptr())
+        if 'grouped' in name:
+            eng.search_grouped(f, 70, n, B, norm)            # the FDMA channel loop as Doppler groups (host results, synchronises)
+        else:
+            eng.search_device(f, n, B, norm, 0, rec.data_ptr())
     step(); torch.cuda.synchronize()
     reps = 3
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

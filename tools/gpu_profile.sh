@@ -5,7 +5,7 @@
 set -x
 mkdir -p gpurun_out
 TAG=${1:-r02}
-B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_corr -s 80 -c 2 -f \
