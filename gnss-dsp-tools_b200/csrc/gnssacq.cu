@@ -686,13 +686,13 @@ int encode_tensor_map_3d_u64(TensorMap* out, const void* base, const unsigned lo
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static_assert(sizeof(CUtensorMap) == sizeof(TensorMap), "tensor map size");
-  static encode_fn encode = nullptr;
-  if (!encode) {
+  static const encode_fn encode = [] {                       // resolved once per process (thread-safe)
     cudaDriverEntryPointQueryResult q;
     void* fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
-    encode = reinterpret_cast<encode_fn>(fn);
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+    return reinterpret_cast<encode_fn>(fn);
+  }();
+  if (!encode) return -1;
   const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
   const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
   const cuuint32_t bx[3] = {box[0], box[1], box[2]};
@@ -734,25 +734,32 @@ struct NcclApi {
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
-NcclApi g_nccl;
-int nccl_api(NcclApi** out) {
-  if (!g_nccl.lib) {
+// resolved once per process (thread-safe: function-local static); lib == nullptr if NCCL could not be loaded
+const NcclApi& nccl_load(std::string* why) {
+  static std::string err;
+  static const NcclApi api = [] {
+    NcclApi a;
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-      g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-      if (g_nccl.lib) break;
+      a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.lib) break;
     }
-    if (!g_nccl.lib) return fail(GNSSACQ_ESTATE, std::string("NCCL is not available: ") + dlerror());
-    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
-    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
-    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
-    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(g_nccl.lib, "ncclAllGather"));
-    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
-      g_nccl = NcclApi();
-      return fail(GNSSACQ_ESTATE, "libnccl lacks an expected entry point");
-    }
-  }
-  *out = &g_nccl;
+    if (!a.lib) { const char* e = dlerror(); err = std::string("NCCL is not available: ") + (e ? e : "dlopen failed"); return a; }
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.lib, "ncclAllGather"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather) { a = NcclApi(); err = "libnccl lacks an expected entry point"; }
+    return a;
+  }();
+  if (why) *why = err;
+  return api;
+}
+int nccl_api(const NcclApi** out) {
+  std::string why;
+  const NcclApi& api = nccl_load(&why);
+  if (!api.lib) return fail(GNSSACQ_ESTATE, why);
+  *out = &api;
   return 0;
 }
 int nccl_fail(const NcclApi* api, const char* what, int rc) {
@@ -765,7 +772,7 @@ extern "C" {
 
 int gnssacq_nccl_unique_id(void* id128) {
   if (!id128) return fail(GNSSACQ_EINVAL, "NULL argument");
-  NcclApi* api;
+  const NcclApi* api;
   if (int rc = nccl_api(&api)) return rc;
   NcclUniqueId id;
   if (int rc = api->GetUniqueId(&id)) return nccl_fail(api, "ncclGetUniqueId", rc);
@@ -775,7 +782,7 @@ int gnssacq_nccl_unique_id(void* id128) {
 
 int gnssacq_nccl_init(gnssacq_t* h, const void* id128, int32_t rank, int32_t world) {
   if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(GNSSACQ_EINVAL, "bad communicator arguments");
-  NcclApi* api;
+  const NcclApi* api;
   if (int rc = nccl_api(&api)) return rc;
   CU(cudaSetDevice(h->device));
   if (h->nccl_comm) { api->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
@@ -808,7 +815,7 @@ int gnssacq_search_sharded(gnssacq_t* h, const double* nco_freq, int32_t D, int3
     CU(cudaStreamSynchronize(h->stream));
   }
   if (world > 1) {
-    NcclApi* api;
+    const NcclApi* api;
     if (int rc = nccl_api(&api)) return rc;
     if (int rc = api->AllGather(h->d_rec.p, h->d_allrec.p, (size_t)R * 4, /*ncclInt32*/ 2, h->nccl_comm, h->stream))
       return nccl_fail(api, "ncclAllGather", rc);
@@ -876,7 +883,7 @@ int gnssacq_destroy(gnssacq_t* h) {
     if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
     h->d_scratch_lane[l].release();
   }
-  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  if (h->nccl_comm) { const NcclApi& api = nccl_load(nullptr); if (api.CommDestroy) api.CommDestroy(h->nccl_comm); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
