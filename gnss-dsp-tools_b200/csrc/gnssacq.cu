@@ -578,16 +578,20 @@ int correlate_chunk(gnssacq* h, int B, int D, int d0, int dc, int Uc, int n_lags
           CU(cudaStreamWaitEvent(h->stream, h->ev_join[l], 0));
         }
       } else {
+        // one stream: the handle's scratch, or — when the search as a whole alternates over lanes and only this
+        // (last, short) Doppler chunk does not — the first lane's buffer, which has the same size
+        float2* scr1 = h->d_scratch.cap >= (size_t)std::min(Uc, units) * B * p.N * sizeof(float2) ? h->d_scratch.as<float2>()
+                                                                                                 : h->d_scratch_lane[0].as<float2>();
         for (int u0 = 0; u0 < units; u0 += Uc) {
           const int uc = std::min(Uc, units - u0);
           {
             StageTimer timer(h, kStageCorrRows, 1);
             GNSSACQ_LAUNCH(kr, dim3(nrt, B, uc), dim3(tr), smr, h->stream,
-                           p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, h->d_scratch.as<float2>());
+                           p, h->d_X.as<float2>(), h->d_C.as<float2>(), R, B, u0, scr1);
           }
           StageTimer timer(h, kStageCorrCols, 1);
           GNSSACQ_LAUNCH(kc, dim3(uc, ntiles), dim3(tcn), smc, h->stream, p,
-                         h->d_scratch.as<float2>(), R, B, D, d0, u0, n_lags, scale, ntiles,
+                         scr1, R, B, D, d0, u0, n_lags, scale, ntiles,
                          h->d_parts.as<Part>(), d_qdump, h->d_hint.as<unsigned>());
           h->launches += 2;
         }
@@ -653,10 +657,10 @@ int run_search(gnssacq* h, const double* nco_freq, int D, int stride, int B, int
     if (h->force_uc > 0) uc = (size_t)h->force_uc;
     Uc = (int)std::max<size_t>(1, std::min<size_t>((size_t)R * Dc, uc));
     Uc = std::min(Uc, 65535);
-    if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
-    if (h->overlap && R * Dc > Uc)
+    if (h->overlap && (long long)R * Dc > Uc) {          // chunks alternate over the lanes' own buffers
       for (int l = 0; l < h->nlanes; ++l)
         if (int rc = h->d_scratch_lane[l].ensure((size_t)Uc * B * tbytes)) return rc;
+    } else if (int rc = h->d_scratch.ensure((size_t)Uc * B * tbytes)) return rc;
   }
   for (int d0 = 0; d0 < D; d0 += Dc) {
     const int dc = std::min(Dc, D - d0);
@@ -1227,7 +1231,7 @@ int gnssacq_mix(gnssacq_t* h, float* iq, int64_t n, double f, double p) {
   const long long df = (long long)floor(f * scale);
   if (int rc = h->d_tmp.ensure((size_t)n * sizeof(float2))) return rc;
   CU(cudaMemcpyAsync(h->d_tmp.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  const int blocks = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, 148 * 16);
+  const int blocks = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)h->num_sms * 16);
   GNSSACQ_LAUNCH(k_mix, dim3(blocks), dim3(kThreads), 0, h->stream, h->d_tmp.as<float2>(), (long long)n,
                  (unsigned long long)dp0, (unsigned long long)df, h->d_nco_f64.as<double2>());
   h->launches += 1;

@@ -324,3 +324,16 @@ def test_30690_coprime_split_341x90_with_ragged_column_tiles(eng):
         assert eng.kernel_variant() == 59
     finally:
         eng.set_option('v3', 1)
+
+
+def test_short_last_doppler_chunk_uses_a_lane_buffer(eng):
+    """A search whose Doppler list splits into a long chunk (alternating over the lanes' scratch buffers) and a
+    short last one (single stream): the short chunk must find a scratch buffer although the handle's own is
+    not allocated for lane searches."""
+    eng.set_option('xchunk_mb', 1)                  # 16384-point spectra: 8 Doppler bins per chunk
+    eng.set_option('units_per_chunk', 4)
+    try:
+        _case(eng, 8192, True, False, False, 1, (-800, 1000, 200), 8.192e6, nprn=3)     # 9 bins: chunks of 8 (24 units, lanes) + 1 (3 units)
+    finally:
+        eng.set_option('xchunk_mb', 512)
+        eng.set_option('units_per_chunk', 0)
