@@ -108,7 +108,7 @@ struct gnssacq {
   DevBuf d_hint;                                     // per (replica, Doppler) unit: best value reported so far (peak-search floor)
   int v3tab_key[4] = {0, 0, 0, 0};                   // (N, RB, PB, CW) the table was built for
   int v3_ntiles = 0;
-  struct LaneMap { TensorMap map; const void* base = nullptr; long long slots = 0; int NP = 0, CW = 0; } v3_map[kMaxLanes + 1];
+  struct LaneMap { TensorMap map; const void* base = nullptr; long long slots = 0; int NP = 0, CW = 0, F1 = 0, F2 = 0; } v3_map[kMaxLanes + 1];
   int small_ctas = 3;                 // bit 0: 8-row / 128-160-thread rows kernel, bit 1: 128-thread columns kernel
   int force_n1 = 0;                   // tuning: force the four-step split N = n1 * (N/n1)
   unsigned long long disabled_radices = 0;   // tuning: stage radices the planner may not use
@@ -384,13 +384,13 @@ int v3_upload_tables(gnssacq* h, const V3Setup& v) {
 
 int v3_map_for(gnssacq* h, const V3Setup& v, int which, const void* base, long long slots) {
   gnssacq::LaneMap& m = h->v3_map[which];
-  if (m.base == base && m.slots == slots && m.NP == v.NP && m.CW == v.c.CW) return 0;
+  if (m.base == base && m.slots == slots && m.NP == v.NP && m.CW == v.c.CW && m.F1 == v.F1 && m.F2 == v.F2) return 0;
   const unsigned long long dims[3] = {(unsigned long long)v.NP, (unsigned long long)v.F1, (unsigned long long)v.F2 * (unsigned long long)slots};
   const unsigned long long strides[2] = {(unsigned long long)v.NP * sizeof(float2), (unsigned long long)v.NP * sizeof(float2) * v.F1};
   const unsigned box[3] = {(unsigned)v.c.CW, (unsigned)v.F1, (unsigned)v.F2};
   const int rc = encode_tensor_map_3d_u64(&m.map, base, dims, strides, box);
   if (rc != 0) return fail(GNSSACQ_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(rc));
-  m.base = base; m.slots = slots; m.NP = v.NP; m.CW = v.c.CW;
+  m.base = base; m.slots = slots; m.NP = v.NP; m.CW = v.c.CW; m.F1 = v.F1; m.F2 = v.F2;
   return 0;
 }
 
