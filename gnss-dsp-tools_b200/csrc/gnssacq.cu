@@ -240,6 +240,7 @@ int upload_plan(gnssacq* h, int N) {
   h->dp.fpos1 = h->d_maps.as<int>() + hp.N1 + 3 * hp.N2;
   h->dp.fpos2 = h->dp.fpos1 + hp.N1;
   h->hp = std::move(hp);
+  h->v3tab_key[0] = 0;                               // tables derived from the previous plan are stale
   return 0;
 }
 
