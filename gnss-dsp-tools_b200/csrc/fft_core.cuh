@@ -15,6 +15,7 @@
 #pragma once
 #include "cuda_compat.h"
 #include <type_traits>
+#include <utility>
 
 namespace acq {
 
@@ -391,6 +392,138 @@ __device__ __forceinline__ void prime_outputs(const float2 x0, const float2* a, 
       emit(P - k, make_float2(re[t].x - im[t].y, re[t].y + im[t].x));
     });
   });
+}
+
+// ---------------------------------------------------------------- radix 31 as two 15-point cyclic convolutions
+// The symmetric-sum butterfly above spends (P-1)^2 = 900 real FMAs on 31 points: two 15 x 15 real matrices
+// (cos on a[j] = x[j] + x[31-j], sin on b[j] = x[j] - x[31-j]) applied to complex vectors. Both matrices are
+// convolutions in disguise (Rader): 3 generates (Z/31)*, and modulo +-1 that group is cyclic of order 15, so
+// with class index m (representative jr[m] = +-3^m mod 31 in 1..15)
+//     cos(2 pi jr[m] jr[n] / 31) = hc[(m + n) mod 15],         hc[t] = cos(2 pi 3^t / 31)
+//     sin(2 pi jr[m] jr[n] / 31) = sg[m] sg[n] hs[(m + n) mod 15], hs[t] = (-1)^t sin(2 pi 3^t / 31),
+// sg[m] = sign(3^m mod 31 <= 15) (-1)^m (3^15 = -1 makes the sine sequence anti-periodic; 15 is odd, so the
+// alternating sign turns it periodic). Signs are free: b[j] is formed with its operands swapped, and a
+// negative output sign exchanges outputs k and 31 - k. A 15-point cyclic convolution is a 3 x 5
+// two-dimensional one (CRT on the index); along the 3-point axis Winograd's algorithm needs 4 block products
+// instead of 9, the blocks being 5 x 5 matrix-vector products done with FMAs:
+//     S = x0 + x1 + x2, u = x0 - x2, v = x1 - x2, w = u + v                       (x_i: 5-vectors, 25 adds)
+//     t = Hs S,  m = t + H1' w,  y0 = m + (H0' - H1') u,  y1 = m + (H2' - H1') v    (4 x 25 FMAs)
+//     y2 = 3 t - y0 - y1                                                           (10 operations)
+// with Hs = (H0 + H1 + H2) / 3 and Hi' = Hi - Hs: 135 packed operations per convolution instead of 225,
+// 270 + 5 per butterfly instead of 450 + 15. Block 2 is delivered NEGATED in both convolutions
+// (-(y0 - 3 t + y1): no packed negation exists), i.e. outputs of block 2 are the negatives of the DFT outputs —
+// the callers take |.| of them.
+__host__ __device__ constexpr int r31_crt(int a3, int a5) { return (10 * a3 + 6 * a5) % 15; }
+__host__ __device__ constexpr int r31_pow3(int m) { int g = 1; for (int i = 0; i < m; ++i) g = (g * 3) % 31; return g; }
+__host__ __device__ constexpr int r31_rep(int m) { const int g = r31_pow3(m); return g <= 15 ? g : 31 - g; }          // jr[m]
+__host__ __device__ constexpr int r31_sign(int m) { return ((r31_pow3(m) <= 15) ? 1 : -1) * ((m & 1) ? -1 : 1); }      // sg[m]
+__host__ __device__ constexpr int r31_class(int j) { for (int m = 0; m < 15; ++m) if (r31_rep(m) == j) return m; return -1; }
+// b[j] must be handed over as sg[class(j)] * (x[j] - x[31-j]): true when the operands have to be swapped
+__host__ __device__ constexpr bool r31_flip_b(int j) { return r31_sign(r31_class(j)) < 0; }
+// digit (output index of the 31-point transform) of value t of block n3: values come in pairs, pair p = t / 2 is
+// class n = crt(n3, p); the even value is re + i*im' (im' = the sine convolution as delivered), the odd one re - i*im'
+__host__ __device__ constexpr int r31_digit(int n3, int t) {
+  const int n = r31_crt(n3, t / 2), k = r31_rep(n);
+  return ((t & 1) == 0) == (r31_sign(n) > 0) ? k : 31 - k;      // caller's convention: output k = re + i*im_k, im_k = sg[n] im'
+}
+#ifdef GNSSACQ_NO_RADER31
+constexpr bool kRader31On = false;            // A/B builds: the (P-1)^2 butterfly everywhere
+#else
+constexpr bool kRader31On = true;
+#endif
+// compile-time digit lists handed to the epilogues
+template <int N> struct IntArray { int v[N]; int n; };
+template <int... Q> __host__ __device__ constexpr IntArray<sizeof...(Q)> seq_array(std::integer_sequence<int, Q...>) {
+  return IntArray<sizeof...(Q)>{{Q...}, (int)sizeof...(Q)};
+}
+template <int N3, int... T> __host__ __device__ constexpr auto r31_block_digits(std::integer_sequence<int, T...>) {
+  return std::integer_sequence<int, r31_digit(N3, T)...>{};
+}
+// pairs k0, k0+1, ...: even value = output k, odd value = output P - k
+template <int P, int K0, int... T> __host__ __device__ constexpr auto prime_pair_digits(std::integer_sequence<int, T...>) {
+  return std::integer_sequence<int, ((T & 1) ? P - (K0 + T / 2) : K0 + T / 2)...>{};
+}
+struct Rader31Tab { float hc[4][5], hs[4][5]; };
+__host__ __device__ constexpr Rader31Tab make_rader31_tab() {
+  Rader31Tab r{};
+  for (int pass = 0; pass < 2; ++pass)
+    for (int t5 = 0; t5 < 5; ++t5) {
+      double h[3] = {0.0, 0.0, 0.0};
+      for (int t3 = 0; t3 < 3; ++t3) {
+        const int t = r31_crt(t3, t5), g = r31_pow3(t);
+        h[t3] = pass ? ((t & 1) ? -1.0 : 1.0) * cx_sin(cx_angle(g, 31)) : cx_cos(cx_angle(g, 31));
+      }
+      const double s = (h[0] + h[1] + h[2]) / 3.0;
+      float (*o)[5] = pass ? r.hs : r.hc;
+      o[0][t5] = (float)s;
+      o[1][t5] = (float)(h[1] - s);
+      o[2][t5] = (float)(h[0] - h[1]);
+      o[3][t5] = (float)(h[2] - h[1]);
+    }
+  return r;
+}
+template <int P> constexpr Rader31Tab kRader31 = make_rader31_tab();
+
+// y[n5] = init[n5] + sum_m5 M[K][(m5 + n5) mod 5] x[m5]: five interleaved chains of five packed FMAs
+template <bool SIN, int K>
+__device__ __forceinline__ void r31_block(const float2* x, const float2* init, float2* y) {
+#pragma unroll
+  for (int n5 = 0; n5 < 5; ++n5) y[n5] = init[n5];
+  static_for<0, 5>([&](auto M5) {
+    static_for<0, 5>([&](auto N5) {
+      constexpr int m5 = decltype(M5)::value, n5 = decltype(N5)::value;
+      constexpr float c = SIN ? kRader31<31>.hs[K][(m5 + n5) % 5] : kRader31<31>.hc[K][(m5 + n5) % 5];
+      y[n5] = cfma_real(c, x[m5], y[n5]);
+    });
+  });
+}
+// One convolution. in(integral_constant m) = input of class m; blk(integral_constant n3, y) receives block n3
+// (classes crt(n3, 0..4)), block 2 negated; sums(S) sees the five column sums (their total is sum_m in(m)).
+template <bool SIN, class In, class Sums, class Blk>
+__device__ __forceinline__ void r31_conv(const float2 init, In&& in, Sums&& sums, Blk&& blk) {
+  float2 S[5], u[5], v[5], w[5];
+  static_for<0, 5>([&](auto M5) {
+    constexpr int m5 = decltype(M5)::value;
+    const float2 x0 = in(std::integral_constant<int, r31_crt(0, m5)>{});
+    const float2 x1 = in(std::integral_constant<int, r31_crt(1, m5)>{});
+    const float2 x2 = in(std::integral_constant<int, r31_crt(2, m5)>{});
+    S[m5] = cadd(cadd(x0, x1), x2);
+    u[m5] = csub(x0, x2);
+    v[m5] = csub(x1, x2);
+    w[m5] = cadd(u[m5], v[m5]);
+  });
+  sums(S);
+  float2 i5[5], t[5], m[5], y[5], d[5];
+#pragma unroll
+  for (int n5 = 0; n5 < 5; ++n5) i5[n5] = init;
+  r31_block<SIN, 0>(S, i5, t);
+  r31_block<SIN, 1>(w, t, m);
+  r31_block<SIN, 2>(u, m, y);
+  blk(std::integral_constant<int, 0>{}, y);
+#pragma unroll
+  for (int n5 = 0; n5 < 5; ++n5) d[n5] = cfma_real(-3.f, t[n5], y[n5]);      // y0 - 3 t
+  r31_block<SIN, 3>(v, m, y);
+  blk(std::integral_constant<int, 1>{}, y);
+#pragma unroll
+  for (int n5 = 0; n5 < 5; ++n5) y[n5] = cadd(d[n5], y[n5]);                 // -(y2)
+  blk(std::integral_constant<int, 2>{}, y);
+}
+// All 31 outputs of the butterfly whose inputs are x0, a[j] = x[j] + x[31-j] and
+// bs[j] = (r31_flip_b(j) ? x[31-j] - x[j] : x[j] - x[31-j]), j = 1..15.
+// dc(s0): output 0 = x0 + sum a[j]. batch(integral_constant n3, re, im): for p = 0..4 the pair
+// (re[p] + i*im[p], re[p] - i*im[p]) in the (re.x - im.y, re.y + im.x) sense are the outputs with digits
+// r31_digit(n3, 2p), r31_digit(n3, 2p + 1) — negated for n3 == 2.
+template <class DC, class Batch>
+__device__ __forceinline__ void rader31_outputs(const float2 x0, const float2* a, const float2* bs, DC&& dc, Batch&& batch) {
+  float2 yc[3][5];
+  r31_conv<false>(x0, [&](auto M) { return a[r31_rep(decltype(M)::value)]; },
+                  [&](const float2* S) { dc(cadd(cadd(cadd(x0, S[0]), cadd(S[1], S[2])), cadd(S[3], S[4]))); },
+                  [&](auto N3, const float2* y) {
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) yc[decltype(N3)::value][p] = y[p];
+                  });
+  r31_conv<true>(make_float2(0.f, 0.f), [&](auto M) { return bs[r31_rep(decltype(M)::value)]; }, [](const float2*) {},
+                 [&](auto N3, const float2* y) { batch(N3, yc[decltype(N3)::value], y); });
 }
 
 // NOTW: prime-factor transform, no stage twiddles.

@@ -254,8 +254,12 @@ __device__ __forceinline__ void cols_v3_inputs(const float2* tile, int i, int tc
     constexpr int j = decltype(J)::value;
     const float2 u = p[j * m0 * CW], w = p[(R0 - j) * m0 * CW];
     a[j] = cadd(u, w);
-    bq[j] = csub(u, w);
-    s0 = cadd(s0, a[j]);
+    if constexpr (kRader31On && R0 == 31) {
+      bq[j] = r31_flip_b(j) ? csub(w, u) : csub(u, w);         // signed for the sine convolution; output 0 comes from its column sums
+    } else {
+      bq[j] = csub(u, w);
+      s0 = cadd(s0, a[j]);
+    }
   });
 }
 
@@ -277,16 +281,17 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
   int n1i = i;
   if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
   float floor_ = fmaxf(fmaxf(best, hint), 0.f);
-  // NB outputs v[t] with digit qof(t): magnitudes, accumulation over blocks, sum, peak candidates
-  auto sink = [&](auto NBc, auto qof, const float2* v) {
-    constexpr int NB = decltype(NBc)::value;
+  // outputs v[t] with digits Q...: magnitudes, accumulation over blocks, sum, peak candidates
+  auto sink = [&](auto digits, const float2* v) {
+    constexpr auto dg = seq_array(decltype(digits){});
+    constexpr int NB = (int)dg.n;
     float acc[NB];
 #pragma unroll
     for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(fmaf(v[t].x, v[t].x, v[t].y * v[t].y));
     if constexpr (MULTI) {
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
-        float* q1 = qp + qof(t) * m0 * CW;
+        float* q1 = qp + dg.v[t] * m0 * CW;
         if (b > 0) acc[t] += *q1;
         if (!last) *q1 = acc[t];
       }
@@ -304,7 +309,7 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         if (acc[t] >= floor_) {
-          int q = qof(t);
+          int q = dg.v[t];
 #if defined(__CUDA_ARCH__)
           asm volatile("" : "+r"(q));
 #endif
@@ -320,20 +325,34 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
     }
     if constexpr (DUMP) {
 #pragma unroll
-      for (int t = 0; t < NB; ++t) qd[lag_of(n1i, qof(t))] = acc[t] * scale;
+      for (int t = 0; t < NB; ++t) qd[lag_of(n1i, dg.v[t])] = acc[t] * scale;
     }
   };
-  sink(std::integral_constant<int, 1>{}, [](int) { return 0; }, &s0);
-  prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
-    constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
-    float2 v[2 * nk];
+  if constexpr (kRader31On && R0 == 31) {
+    // two 15-point convolutions (fft_core.cuh); block 2 arrives negated, |.| does not see it
+    rader31_outputs(x0, a, bq, [&](const float2 dc) { sink(std::integer_sequence<int, 0>{}, &dc); },
+                    [&](auto N3, const float2* re, const float2* im) {
+                      float2 v[10];
 #pragma unroll
-    for (int t = 0; t < nk; ++t) {
-      v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
-      v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
-    }
-    sink(std::integral_constant<int, 2 * nk>{}, [](int t) { return (t & 1) ? R0 - (k0 + t / 2) : k0 + t / 2; }, v);
-  });
+                      for (int t = 0; t < 5; ++t) {
+                        v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);
+                        v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);
+                      }
+                      sink(r31_block_digits<decltype(N3)::value>(std::make_integer_sequence<int, 10>{}), v);
+                    });
+  } else {
+    sink(std::integer_sequence<int, 0>{}, &s0);
+    prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
+      constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
+      float2 v[2 * nk];
+#pragma unroll
+      for (int t = 0; t < nk; ++t) {
+        v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
+        v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
+      }
+      sink(prime_pair_digits<R0, k0>(std::make_integer_sequence<int, 2 * nk>{}), v);
+    });
+  }
 }
 
 template <class S, bool MULTI, bool DUMP, int CW, int THREADS>
