@@ -226,6 +226,99 @@ k_corr_rows_v4(DevPlan pl, const float2* __restrict__ X, const float2* __restric
   if (leader) bulk_wait_all<0>();                              // shared memory must outlive the last stores
 }
 
+// =========================================================================== rows kernel, two roles
+// In k_corr_rows_v3 stage B (T*RA butterflies of ~400 instructions) runs on half of the threads stage A
+// (T*RB butterflies of ~190) uses, between two block barriers: a third of the warp-time of a CTA is spent
+// waiting (ncu r04a: 34 % barrier stalls), and k_corr_rows_v4's alternating halves do not change that sum
+// (each half still waits for the other half's share of stage A). Here the two stages belong to two warps
+// for good: warp 0 multiplies and runs stage A of BOTH rows of a 2-row tile (two butterflies per lane),
+// warp 1 runs stage B (2 * 15 = 30 lanes) and issues the bulk store — equal instruction counts per
+// (Doppler, block) pair, and A(it+1) overlaps B(it) through the two exchange buffers. No block barrier:
+//   xfull[s]  spectra tile of ring slot s landed (copy-engine transaction count)
+//   efull[e]  the 32 lanes of warp 0 have written their stage-A outputs into exchange buffer e
+//   efree[e]  the bulk store that read exchange buffer e has drained it (lane 0 of warp 1, at the start of the next pair)
+// Same arithmetic as k_corr_rows_v3: bit-identical scratch.
+template <class S> __host__ __device__ constexpr size_t rows_v6_smem() {
+  return 2 * (size_t)2 * S::F * sizeof(float2) + 2 * (size_t)2 * S::radix(0) * v3_pitch(S::radix(1)) * sizeof(float2) + 6 * 8;
+}
+template <class S, int MINCTAS>
+__global__ void __launch_bounds__(64, MINCTAS)
+k_corr_rows_v6(DevPlan pl, const float2* __restrict__ X, const float2* __restrict__ C, ChunkV3 ck, int B,
+               float2* __restrict__ scratch) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2 && S::kPfa, "two coprime stages");
+  constexpr int T = 2;
+  constexpr int N2 = S::F, RA = S::radix(0), RB = S::radix(1), PB = v3_pitch(RB), NP = RA * PB;
+  static_assert(RB == 32 && T * RA <= 32, "one lane per stage-A column, stage B within one warp");
+  constexpr int XT = T * N2, ET = T * NP;
+  float2* xbuf = smem;
+  float2* ebuf = smem + 2 * XT;
+  unsigned long long* xfull = reinterpret_cast<unsigned long long*>(ebuf + 2 * ET);
+  unsigned long long* efull = xfull + 2;
+  unsigned long long* efree = xfull + 4;
+  const int N = pl.N, N1 = pl.N1;
+  const int row0 = blockIdx.x * T;
+  const int nrows = imin(T, N1 - row0);
+  const int r = ck.r0 + blockIdx.y;
+  const int nall = ck.G * B, per = (nall + gridDim.z - 1) / gridDim.z;
+  const int it0 = blockIdx.z * per, nit = imin(per, nall - it0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned xbytes = (unsigned)nrows * N2 * sizeof(float2), ebytes = (unsigned)nrows * NP * sizeof(float2);
+
+  auto issue = [&](int it) {                                   // spectra tile of pair `it` -> ring slot it & 1
+    const int g = it0 + it;
+    const float2* src = X + ((long long)(ck.dd0 + g / B) * B + g % B) * N + (long long)row0 * N2;
+    mbar_arrive_expect(&xfull[it & 1], xbytes);
+    bulk_g2s(xbuf + (it & 1) * XT, src, xbytes, &xfull[it & 1]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&xfull[s], 1); mbar_init(&efull[s], 32); mbar_init(&efree[s], 1); }
+    mbar_fence_init();
+    for (int it = 0; it < 2 && it < nit; ++it) issue(it);
+  }
+  __syncthreads();                                             // barrier initialisation visible to both warps
+
+  if (warp == 0) {
+    // stage A: lane = contiguous digit b, both rows; the replica-spectrum values stay in registers
+    float2 c0[RA], c1[RA];
+    const float2* cp = C + (long long)r * N + (long long)row0 * N2 + lane;
+#pragma unroll
+    for (int a = 0; a < RA; ++a) c0[a] = __ldg(&cp[a * RB]);
+#pragma unroll
+    for (int a = 0; a < RA; ++a) c1[a] = nrows > 1 ? __ldg(&cp[N2 + a * RB]) : make_float2(0.f, 0.f);
+    for (int it = 0; it < nit; ++it) {
+      const int e = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      float2* et = ebuf + e * ET;
+      mbar_wait(&xfull[e], ph);
+      if (it >= 2) mbar_wait(&efree[e], ph ^ 1u);              // the store of pair it-2 has drained this buffer
+      rows_v3_stage_a<S>(xbuf + e * XT, et, c0, 0, lane);
+      if (nrows > 1) rows_v3_stage_a<S>(xbuf + e * XT, et, c1, 1, lane);
+      __syncwarp();                                            // every lane is done with ring slot e
+      if (lane == 0 && it + 2 < nit) { fence_async_smem(); issue(it + 2); }
+      mbar_arrive(&efull[e]);
+    }
+  } else {
+    const bool act_b = lane < nrows * RA;                      // stage-B butterfly: group lane = row * RA + a'
+    for (int it = 0; it < nit; ++it) {
+      const int e = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      float2* et = ebuf + e * ET;
+      mbar_wait(&efull[e], ph);
+      if (lane == 0 && it >= 1) { bulk_wait_read<0>(); mbar_arrive(&efree[e ^ 1]); }   // my store of pair it-1 has read its buffer
+      if (act_b) { rows_v3_stage_b<S>(et, lane); fence_async_smem(); }
+      __syncwarp();
+      if (lane == 0) {
+        const int g = it0 + it;
+        const int slot = v3_slot(ck, B, r, ck.dd0 + g / B, g % B);
+        bulk_s2g(scratch + ((long long)slot * N1 + row0) * NP, et, ebytes);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait_all<0>();                         // shared memory must outlive the last stores
+  }
+}
+
 // =========================================================================== cols kernel
 // ring slots start on 128-byte boundaries (tensor-map copies need it)
 template <class S, int CW> __host__ __device__ constexpr int cols_v3_slot() { return (S::F * CW + 15) / 16 * 16; }   // float2 per slot
@@ -404,36 +497,68 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
   float* qs = reinterpret_cast<float*>(smem + 2 * SLOT);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v3_smem<S, MULTI, CW>() - 16);
   const int N = pl.N;
-  const int tid = threadIdx.x, tc = tid & (CW - 1), tb = tid / CW;
-  constexpr int nb = THREADS / CW;
-  const int ntasks = ck.Rc * ck.G * ntiles;
-  // Tasks are tile-major (task = ct * units + ul): the tiles of one unit are spread over the waves of
-  // the persistent grid, so all but the first carry a peak-search floor from the unit's earlier tiles.
+  const int tid = threadIdx.x, tc = tid & (CW - 1);
+  static_assert(THREADS % 32 == 0, "whole warps");
+  constexpr int NW = THREADS / 32;
+  // per-warp results of a finished tile; thread 0 folds them behind the next block barrier (two sets: the
+  // warps of the next tile write the other one)
+  __shared__ unsigned long long s_key[2][NW];
+  __shared__ float s_sum[2][NW];
+  // Tasks are tile-major (task = ct * units + ul, ul = ur * G + ud): the tiles of one unit are spread over the
+  // waves of the persistent grid, so all but the first carry a peak-search floor from the unit's earlier
+  // tiles. A CTA's tasks are gridDim.x apart; (ct, ur, ud) advance by carries instead of divisions.
   const int nunits = ck.Rc * ck.G;
-  auto issue = [&](int task, int b, int slot) {                // thread 0
-    const int ct = task / nunits, ul = task - ct * nunits;
+  const int step_ct = (int)gridDim.x / nunits, step_ul = (int)gridDim.x - step_ct * nunits;
+  const int step_ur = step_ul / ck.G, step_ud = step_ul - step_ur * ck.G;
+  int ct = (int)blockIdx.x / nunits, ur, ud;
+  { const int ul = (int)blockIdx.x - ct * nunits; ur = ul / ck.G; ud = ul - ur * ck.G; }
+  auto issue = [&](int ct_, int ul, int b, int slot) {         // thread 0
     mbar_arrive_expect(&full[slot], (unsigned)(TILE * sizeof(float2)));
-    tma_load_3d(smem + slot * SLOT, &map, __ldg(&tile_col0[ct]), 0, (ul * B + b) * zmul, &full[slot]);
+    tma_load_3d(smem + slot * SLOT, &map, __ldg(&tile_col0[ct_]), 0, (ul * B + b) * zmul, &full[slot]);
   };
-  int task = blockIdx.x, b = 0;
+  int b = 0;
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_fence_init();
     tma_prefetch_map(&map);
-    if (task < ntasks) issue(task, 0, 0);
+    if (ct < ntiles) issue(ct, ur * ck.G + ud, 0, 0);
   }
   __syncthreads();
   float best = -1.f, sum = 0.f, hint = 0.f;
   int bestlag = 0x7fffffff, lagc = -1;
-  for (unsigned seq = 0; task < ntasks; ++seq) {
-    int ntask = task, nblk = b + 1;
-    if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
+  long long pend_unit = -1;                                    // thread 0: finished tile whose part is not written yet
+  int pend_ct = 0, pend_set = 0;
+  auto flush = [&]() {                                         // thread 0, behind a block barrier
+    unsigned long long key = s_key[pend_set][0];
+    float sm = s_sum[pend_set][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { const unsigned long long k2 = s_key[pend_set][w]; key = k2 > key ? k2 : key; sm += s_sum[pend_set][w]; }
+    Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
+    if (key != 0ull) {
+      // the hint must be bit-exactly a value that occurred, so the search runs on unscaled values; scaling by
+      // 1/N is monotonic: order and ties of the keys are those of the scaled values
+      const unsigned vb = (unsigned)(key >> 32);
+      p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
+      atomicMax(&unit_hint[pend_unit], vb);
+    }
+    parts[pend_unit * ntiles + pend_ct] = p;
+    pend_unit = -1;
+  };
+  for (unsigned seq = 0; ct < ntiles; ++seq) {
+    int nct = ct, nur = ur, nud = ud, nblk = b + 1;
+    if (nblk == B) {
+      nblk = 0;
+      nct += step_ct; nur += step_ur; nud += step_ud;
+      if (nud >= ck.G) { nud -= ck.G; ++nur; }
+      if (nur >= ck.Rc) { nur -= ck.Rc; ++nct; }
+    }
     __syncthreads();                                           // every thread is done with the previous item: its slot is free
-    if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk, (seq + 1) & 1); }
-    const int ct = task / nunits, ul = task - ct * nunits;
-    const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
-    const long long unit = (long long)r * D + d0 + dd;
+    if (tid == 0) {
+      if (nct < ntiles) { fence_async_smem(); issue(nct, nur * ck.G + nud, nblk, (seq + 1) & 1); }
+      if (pend_unit >= 0) flush();
+    }
+    const long long unit = (long long)(ck.r0 + ur) * D + d0 + ck.dd0 + ud;
     const bool last = (b + 1 == B);
     if (b == 0) {
       best = -1.f; sum = 0.f; bestlag = 0x7fffffff;
@@ -447,23 +572,25 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     __syncthreads();
     if (lagc >= 0) cols_v3_last<S, MULTI, DUMP, CW, THREADS>(tile, qs, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
     if (last) {
-      // reduce on the unscaled value (the hint must be bit-exactly a value that occurred); the scaling
-      // by 1/N is monotonic, so the order and the ties of the keys are those of the scaled values
+      // per warp: the sum always, the key only if some lane holds a candidate (rare once the floor is warm)
       unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
-      float s = sum * scale;
-      block_reduce_part(key, s);
-      if (tid == 0) {
-        Part p; p.key = 0ull; p.sum = s; p.pad = 0.f;
-        if (key != 0ull) {
-          const unsigned vb = (unsigned)(key >> 32);
-          p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
-          atomicMax(&unit_hint[unit], vb);
+      float sm = sum * scale;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if (__any_sync(0xffffffffu, key != 0ull)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
+          key = k2 > key ? k2 : key;
         }
-        parts[unit * ntiles + ct] = p;
       }
+      if ((tid & 31) == 0) { s_key[seq & 1][tid >> 5] = key; s_sum[seq & 1][tid >> 5] = sm; }
+      if (tid == 0) { pend_unit = unit; pend_ct = ct; pend_set = (int)(seq & 1); }
     }
-    task = ntask; b = nblk;
+    ct = nct; ur = nur; ud = nud; b = nblk;
   }
+  __syncthreads();
+  if (tid == 0 && pend_unit >= 0) flush();
 }
 
 // =========================================================================== cols kernel, one tile slot

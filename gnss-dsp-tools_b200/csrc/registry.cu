@@ -106,13 +106,17 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
 #define TRY(S, V, T, TH, C, XB)                                                                                   \
   if (variant == V && schedule_matches<S>(s2))                                                                    \
     return RowsV3{k_corr_rows_v3<S, T, TH, C, XB>, TH, T, C, rows_v3_smem<S, T, XB>(), S::radix(0), S::radix(1), v3_pitch(S::radix(1))};
-  TRY(S480, 0, 4, 128, 4, 1) TRY(S480, 1, 8, 256, 1, 2) TRY(S480, 2, 8, 256, 2, 1) TRY(S480, 3, 4, 128, 3, 2)
+  TRY(S480, 5, 4, 128, 4, 1) TRY(S480, 1, 8, 256, 1, 2) TRY(S480, 2, 8, 256, 2, 1) TRY(S480, 3, 4, 128, 3, 2)
   TRY(S220, 0, 8, 160, 3, 2) TRY(S220, 1, 8, 160, 4, 1)
   TRY(S90, 0, 8, 96, 8, 1) TRY(S90, 1, 8, 96, 6, 2)
 #undef TRY
   // balanced kernel (the two halves of the CTA alternate on stage B): 4 warps, stage B = 2 warps
   if (variant == 4 && schedule_matches<S480>(s2))
     return RowsV3{k_corr_rows_v4<S480, 4, 128, 3>, 128, 4, 3, rows_v4_smem<S480, 4>(), S480::radix(0), S480::radix(1), v3_pitch(S480::radix(1))};
+  // default for 480: two roles, warp 0 = stage A of a 2-row tile, warp 1 = stage B + bulk store, no block barrier
+  // (r04d: correlate stage 1.63 -> 1.59 ms per config-2 step against the 4-row x 128-thread kernel, now variant 5)
+  if (variant == 0 && schedule_matches<S480>(s2))
+    return RowsV3{k_corr_rows_v6<S480, 7>, 64, 2, 7, rows_v6_smem<S480>(), S480::radix(0), S480::radix(1), v3_pitch(S480::radix(1))};
   return RowsV3{nullptr, 0, 0, 0, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 9

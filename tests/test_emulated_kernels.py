@@ -209,7 +209,7 @@ def test_large_163680_register_loading_kernels_on_the_coprime_split(eng):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4), (4, 0, 2, 5), (4, 1, 3, 1), (0, 3, 2, 2), (0, 4, 3, 5)])
+@pytest.mark.parametrize('rows,cols,rc,g', [(0, 0, 2, 2), (1, 1, 1, 3), (2, 2, 3, 1), (3, 0, 2, 4), (4, 0, 2, 5), (4, 1, 3, 1), (0, 3, 2, 2), (0, 4, 3, 5), (5, 0, 2, 2), (5, 1, 3, 5)])
 def test_v3_tile_shapes_and_chunk_edges_163680(eng, rows, cols, rc, g):
     """Every instantiated tile shape of the copy-engine-fed pair, with chunk shapes that leave ragged
     edges (3 replicas in chunks of rc, 5 Doppler bins in groups of g)."""

@@ -20,7 +20,8 @@ torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
 rng = np.random.default_rng(0)
 quick = 'quick' in sys.argv[1:]
-args = [a for a in sys.argv[1:] if a != 'quick']
+nofused = 'nofused' in sys.argv[1:]
+args = [a for a in sys.argv[1:] if a not in ('quick', 'nofused')]
 which = args[0] if args else 'all'
 
 CASES = [('cfg2 163680 R32 D80 B1', 163680, False, 32, 80, 1, True),
@@ -61,8 +62,8 @@ for name, n, pad, R, D, B, norm in CASES:
     eng.set_replicas(rep)
     base = dict(v3=0, fused=0, v3_rows=0, v3_cols=0, v3_rc=0, v3_g=0, lanes=2)
     ref = run(name, n, pad, R, D, B, norm, base)
-    nrows = 4 if N == 163680 else 2
-    ncols = 2
+    nrows = 5 if N == 163680 else 2
+    ncols = 5 if N == 163680 else 2
     if quick:
         nrows, ncols = 1, 2
     shapes = [(0, 0), (16, 4), (32, 4), (32, 8), (16, 16), (8, 16)] if B == 1 else [(0, 0), (16, 1), (32, 1), (64, 1)]
@@ -73,11 +74,12 @@ for name, n, pad, R, D, B, norm in CASES:
             print('   !! lags differ from the register-loading kernels')
     # the fused persistent kernel: group shapes, column tiles per ticket, ring depth
     fshapes = [(4, 4), (2, 8), (4, 8), (8, 4), (16, 2)] if B == 1 else [(4, 1), (8, 1), (16, 1)]
-    for (rc, g), tpt, sets in itertools.product(fshapes, (1, 3, 5, 10, 15), (3,)):
+    for (rc, g), tpt, sets in ([] if nofused else itertools.product(fshapes, (1, 3, 5, 10, 15), (3,))):
         got = run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=rc, fused_g=g, fused_sets=sets, fused_tpt=tpt))
         if not np.array_equal(got.view(np.int32)[1::4], ref.view(np.int32)[1::4]):
             print('   !! lags differ from the register-loading kernels')
-    run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=4, fused_g=8, fused_sets=4, fused_tpt=5))
+    if not nofused:
+        run(name, n, pad, R, D, B, norm, dict(v3=1, fused=1, fused_rc=4, fused_g=8, fused_sets=4, fused_tpt=5))
     run(name, n, pad, R, D, B, norm, dict(v3=1, fused=0, fused_rc=0, fused_g=0, fused_sets=3, fused_tpt=0))
     if quick:
         continue
