@@ -480,15 +480,15 @@ def main():
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
-                     'kernel': 'correlate stage = rows kernel k_corr_rows_v3 + columns kernel k_corr_cols_v3 (one logical fused correlate; launches of 128 units alternate over two streams, so the stage is timed as one span)',
+                     'kernel': 'correlate stage = rows kernel k_corr_rows_v6 + columns kernel k_corr_cols_v3 (one logical fused correlate; launches of 128 units alternate over two streams, so the stage is timed as one span)',
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                      'kernel_ms_per_step': corr_ms / K, 'kernel_launches_per_step': corr_launches / K,
                      'stage_ms_per_step': {k: v[0] / K for k, v in stages.items()},
                      # the HBM roofline is the one BASELINE.json asks for; what actually binds (ncu, profiles/README.md):
-                     'binding': 'the FP32 pipe, not HBM: 163680 = 2^5*3*5*11*31 needs radix-31 and radix-11 butterflies, ~80 FP32 lane-cycles '
-                                'per cell-block = 0.90 ms per step at 100 % pipe utilisation (1.14 x the HBM copy peak in algorithmic bytes); '
-                                'ncu: FMA pipe 54 % (columns) / 44 % (rows) busy, DRAM ~60 % of peak while the stage runs '
-                                '(profiles/README.md, profiles/r03d_corr_ncu_summary.txt)'},
+                     'binding': 'the FP32 pipe and issue slots, not HBM: 163680 = 2^5*3*5*11*31 needs radix-31 and radix-11 butterflies; with the '
+                                'radix-31 butterfly run as two 15-point cyclic convolutions (Rader + 3-point Winograd over 5x5 blocks) the stage costs '
+                                '~67 FP32 lane-cycles per cell-block = 0.75 ms per step at 100 % pipe utilisation; ncu: FMA pipe 52 % (columns) / 48 % (rows) '
+                                'busy, issue slots 50 % / 48 %, DRAM 7.7 GB per step (profiles/README.md, profiles/r04e_corr_ncu_summary.txt)'},
     }
     if not args.no_extra:
         line['configs'] = [bench_shape(eng, torch, stream, dev, cfg, peak) for cfg in EXTRA_CONFIGS]
