@@ -353,7 +353,8 @@ V3Setup v3_setup(const gnssacq* h, bool multi, bool dump) {
     } else v.f = FusedKernel{};
   }
   v.NP = v.r.RA * v.r.PB;
-  v.ntiles = (v.r.RB % v.c.CW == 0) ? v.r.RA * (v.r.RB / v.c.CW) : (v.NP + v.c.CW - 1) / v.c.CW;
+  // ragged layouts walk the flat padded row; its last PB - RB columns are pads, a tile of nothing but those is dropped
+  v.ntiles = (v.r.RB % v.c.CW == 0) ? v.r.RA * (v.r.RB / v.c.CW) : (v.NP - (v.r.PB - v.r.RB) + v.c.CW - 1) / v.c.CW;
   // tensor-map boxes are limited to 256 per dimension: N1 = F1 * F2 with the largest F1 <= 256
   for (int f = 1; f <= 256 && f <= h->hp.N1; ++f)
     if (h->hp.N1 % f == 0) v.F1 = f;

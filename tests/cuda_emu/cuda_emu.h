@@ -68,6 +68,12 @@ template <class T> static inline T emu_shfl(T v, int src) {
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, emu_lane ^ m); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, emu_lane + d < 32 ? emu_lane + d : emu_lane); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int s) { return emu_shfl(v, s); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned v = pred ? (1u << emu_lane) : 0u;
+  for (int o = 16; o > 0; o >>= 1) v |= emu_shfl(v, emu_lane ^ o);
+  return v;
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __any_sync(unsigned, int pred) {
   int v = pred ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) v |= emu_shfl(v, emu_lane ^ o);

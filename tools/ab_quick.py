@@ -12,7 +12,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, 'gnss-dsp-tools_b200')]
 import torch
 from gnsstools import _native
 
-CASES = {'cfg2': (163680, False, 32, 80, 1, True), 'cfg4': (30690, True, 64, 70, 20, False), 'cfg3': (81840, True, 72, 360, 1, False)}
+CASES = {'cfg2': (163680, False, 32, 80, 1, True), 'cfg4': (30690, True, 64, 70, 20, False), 'cfg3': (81840, True, 72, 360, 1, False),
+         'e6': (15345, True, 16, 30, 20, False)}
 args = sys.argv[1:]
 case = args.pop(0) if args and args[0] in CASES else 'cfg2'
 sets = [dict((kv.split('=')[0], int(kv.split('=')[1])) for kv in a.split(',') if kv) for a in (args or [''])]
