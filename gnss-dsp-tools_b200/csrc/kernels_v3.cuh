@@ -594,11 +594,15 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
 }
 
 // =========================================================================== cols kernel, one tile slot
-// The radix-31 stage reads its 31 inputs at once and then computes ~700 instructions from registers, so
-// the tile slot is free long before the tile is finished: the next tensor-map copy is issued right after
-// those reads, into the SAME slot. Half the shared memory of k_corr_cols_v3 (more CTAs per SM) and two
-// block barriers per tile instead of four: the per-tile results are reduced per WARP and written as
-// THREADS/32 parts per tile (k_finalize folds whatever number of parts a unit has).
+// The radix-31 stage reads its 31 inputs at once and then computes ~500 instructions from registers, so the tile
+// slot is free long before the tile is finished: the next tensor-map copy is issued as soon as every thread has
+// arrived at the `empty` mbarrier with its inputs in registers, into the SAME slot. Half the shared memory of
+// k_corr_cols_v3, so registers alone decide how many CTAs an SM holds. Same task order, same per-warp parts folded
+// by thread 0 behind the block barrier of the next tile, same arithmetic: bit-identical results.
+// Two things this kernel has to get right (profiles/README.md, r04): the butterfly's inputs must not cross a
+// control-flow merge between the loads and the epilogue (one region, or ptxas spends ~40 registers on re-pairing
+// them), and lanes without a butterfly must arrive BEFORE the others enter that region (a diverged warp runs its
+// active lanes through the whole epilogue first).
 template <class S, bool MULTI, int CW> __host__ __device__ constexpr size_t cols_v5_smem() {
   return (size_t)cols_v3_slot<S, CW>() * sizeof(float2) + (MULTI ? (size_t)S::F * CW * sizeof(float) : 0) + 16;
 }
@@ -608,73 +612,138 @@ k_corr_cols_v5(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
                ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
                Part* __restrict__ parts, float* __restrict__ q_dump, unsigned* __restrict__ unit_hint) {
   GNSSACQ_DYN_SMEM(float2, smem);
-  static_assert(S::NS == 2 && (CW == 8 || CW == 16), "two-stage columns schedule, tile width");
-  constexpr int N1 = S::F, TILE = N1 * CW, SLOT = cols_v3_slot<S, CW>(), NW = THREADS / 32;
+  static_assert(S::NS == 2, "two-stage columns schedule");
+  static_assert(CW == 8 || CW == 16, "tile width");
+  constexpr int N1 = S::F, TILE = N1 * CW, SLOT = cols_v3_slot<S, CW>();
   constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
-  static_assert(THREADS / CW >= m0, "one radix-R0 butterfly per thread");
+  static_assert(THREADS / CW >= m0 && 32 / CW <= m0, "one radix-R0 butterfly per thread; warp 0 holds butterflies only");
   float* qs = reinterpret_cast<float*>(smem + SLOT);
+  // full: the copy engine has filled the slot; empty: every thread has its radix-R0 inputs of the tile in registers
   unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v5_smem<S, MULTI, CW>() - 16);
+  unsigned long long* empty = full + 1;
   const int N = pl.N;
   const int tid = threadIdx.x, tc = tid & (CW - 1), tb = tid / CW;
-  const int nunits = ck.Rc * ck.G, ntasks = nunits * ntiles;
-  auto issue = [&](int task, int b) {                          // thread 0
-    const int ct = task / nunits, ul = task - ct * nunits;
-    mbar_arrive_expect(full, (unsigned)(TILE * sizeof(float2)));
-    tma_load_3d(smem, &map, __ldg(&tile_col0[ct]), 0, (ul * B + b) * zmul, full);
+  static_assert(THREADS % 32 == 0, "whole warps");
+  constexpr int NW = THREADS / 32;
+  // per-warp results of a finished tile; thread 0 folds them behind the next block barrier (two sets: the
+  // warps of the next tile write the other one)
+  __shared__ unsigned long long s_key[2][NW];
+  __shared__ float s_sum[2][NW];
+  // Tasks are tile-major (task = ct * units + ul, ul = ur * G + ud): the tiles of one unit are spread over the
+  // waves of the persistent grid, so all but the first carry a peak-search floor from the unit's earlier
+  // tiles. A CTA's tasks are gridDim.x apart; (ct, ur, ud) advance by carries instead of divisions.
+  struct Pos { int ct, ur, ud, b; };
+  const int nunits = ck.Rc * ck.G;
+  const int step_ct = (int)gridDim.x / nunits, step_ul = (int)gridDim.x - step_ct * nunits;
+  const int step_ur = step_ul / ck.G, step_ud = step_ul - step_ur * ck.G;
+  auto advance = [&](Pos p) -> Pos {                            // next item of this CTA: next block, else next task
+    if (++p.b == B) {
+      p.b = 0;
+      p.ct += step_ct; p.ur += step_ur; p.ud += step_ud;
+      if (p.ud >= ck.G) { p.ud -= ck.G; ++p.ur; }
+      if (p.ur >= ck.Rc) { p.ur -= ck.Rc; ++p.ct; }
+    }
+    return p;
   };
-  int task = blockIdx.x, b = 0;
+  auto issue = [&](const Pos& p) {
+    mbar_arrive_expect(full, (unsigned)(TILE * sizeof(float2)));
+    tma_load_3d(smem, &map, __ldg(&tile_col0[p.ct]), 0, ((p.ur * ck.G + p.ud) * B + p.b) * zmul, full);
+  };
+  Pos cur;
+  cur.ct = (int)blockIdx.x / nunits; cur.b = 0;
+  { const int ul = (int)blockIdx.x - cur.ct * nunits; cur.ur = ul / ck.G; cur.ud = ul - cur.ur * ck.G; }
+  Pos nx = advance(cur);
   if (tid == 0) {
     mbar_init(full, 1);
+    mbar_init(empty, THREADS);
     mbar_fence_init();
     tma_prefetch_map(&map);
-    if (task < ntasks) issue(task, 0);
+    if (cur.ct < ntiles) issue(cur);
   }
   __syncthreads();
   float best = -1.f, sum = 0.f, hint = 0.f;
   int bestlag = 0x7fffffff, lagc = -1;
-  for (unsigned seq = 0; task < ntasks; ++seq) {
-    int ntask = task, nblk = b + 1;
-    if (nblk == B) { nblk = 0; ntask = task + gridDim.x; }
-    const int ct = task / nunits, ul = task - ct * nunits;
-    const int r = ck.r0 + ul / ck.G, dd = ck.dd0 + ul % ck.G;
-    const long long unit = (long long)r * D + d0 + dd;
+  long long pend_unit = -1;                                    // thread 0: finished tile whose part is not written yet
+  int pend_ct = 0, pend_set = 0;
+  auto flush = [&]() {                                         // thread 0, behind a block barrier
+    unsigned long long key = s_key[pend_set][0];
+    float sm = s_sum[pend_set][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { const unsigned long long k2 = s_key[pend_set][w]; key = k2 > key ? k2 : key; sm += s_sum[pend_set][w]; }
+    Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
+    if (key != 0ull) {
+      // the hint must be bit-exactly a value that occurred, so the search runs on unscaled values; scaling by
+      // 1/N is monotonic: order and ties of the keys are those of the scaled values
+      const unsigned vb = (unsigned)(key >> 32);
+      p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
+      atomicMax(&unit_hint[pend_unit], vb);
+    }
+    parts[pend_unit * ntiles + pend_ct] = p;
+    pend_unit = -1;
+  };
+  for (unsigned seq = 0; cur.ct < ntiles; ++seq) {
+    const int sl = (int)(seq & 1);                             // set of per-warp results
+    const unsigned ph = seq & 1u;
+    const int b = cur.b;
+    const long long unit = (long long)(ck.r0 + cur.ur) * D + d0 + ck.dd0 + cur.ud;
     const bool last = (b + 1 == B);
     if (b == 0) {
       best = -1.f; sum = 0.f; bestlag = 0x7fffffff;
-      lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[ct]) + tc]);
-      hint = __uint_as_float(__ldcg(&unit_hint[unit]));
+      lagc = __ldg(&pl.col_lag[__ldg(&tile_col0[cur.ct]) + tc]);  // -1: pad column, takes no part in the epilogue
+      hint = __uint_as_float(__ldcg(&unit_hint[unit]));         // unscaled, exactly a value some tile has seen (may be stale: any lower bound will do)
     }
     float* qd = DUMP ? q_dump + unit * N : nullptr;
-    mbar_wait(full, seq & 1u);
-    cols_v3_first<S, CW, THREADS>(smem);
-    __syncthreads();
-    const bool act = lagc >= 0 && tb < m0;                     // pad columns and spare butterfly slots only keep the barriers
-    float2 a[H + 1], bq[H + 1], x0, s0;
-    if (act) cols_v3_inputs<S, CW>(smem, tb, tc, x0, a, bq, s0);
-    __syncthreads();                                           // every input is in registers: the slot is free
-    if (tid == 0 && ntask < ntasks) { fence_async_smem(); issue(ntask, nblk); }
-    if (act) cols_v3_outputs<S, MULTI, DUMP, CW>(x0, a, bq, s0, tb, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
+    float2* tile = smem;
+    mbar_wait(full, ph);
+    cols_v3_first<S, CW, THREADS>(tile);
+    __syncthreads();                                           // the only block barrier of a tile
+    if (tid == 0 && pend_unit >= 0) flush();                   // every warp has left its results of the previous tile
+    // pad columns and spare butterfly slots only keep the barriers. They arrive BEFORE the others' region: a warp
+    // that diverges runs its active lanes through the whole epilogue first, and the refill below would wait for that.
+    const bool act = lagc >= 0 && tb < m0;
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    // the refill is the duty of the first active lane of warp 0 (warp 0 holds butterflies only, tb < m0), of lane 0 if a
+    // tile has no real column at all: never of a lane that waits while lanes of its own warp still have to arrive
+    const bool refiller = tid < 32 && tid == (actmask ? __ffs((int)actmask) - 1 : 0);
+    auto refill = [&]() {                                      // refill the slot with the next item
+      if (nx.ct < ntiles) {
+        mbar_wait(empty, ph);
+        fence_async_smem();
+        issue(nx);
+      }
+    };
+    if (!act) {
+      mbar_arrive(empty);
+      if (refiller) refill();
+    }
+    if (act) {
+      // one region from the loads to the epilogue: the inputs stay in the register pairs the packed instructions need
+      float2 a[H + 1], bq[H + 1], x0, s0;
+      cols_v3_inputs<S, CW>(tile, tb, tc, x0, a, bq, s0);
+      mbar_arrive(empty);                                 // my inputs are in registers
+      if (refiller) refill();
+      cols_v3_outputs<S, MULTI, DUMP, CW>(x0, a, bq, s0, tb, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
+    }
     if (last) {
+      // per warp: the sum always, the key only if some lane holds a candidate (rare once the floor is warm)
       unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;
       float sm = sum * scale;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
-        sm += __shfl_xor_sync(0xffffffffu, sm, o);
-        key = k2 > key ? k2 : key;
-      }
-      if ((tid & 31) == 0) {
-        Part p; p.key = 0ull; p.sum = sm; p.pad = 0.f;
-        if (key != 0ull) {
-          const unsigned vb = (unsigned)(key >> 32);
-          p.key = ((unsigned long long)__float_as_uint(__uint_as_float(vb) * scale) << 32) | (key & 0xffffffffull);
-          atomicMax(&unit_hint[unit], vb);
+      for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if (__any_sync(0xffffffffu, key != 0ull)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
+          key = k2 > key ? k2 : key;
         }
-        parts[(unit * ntiles + ct) * NW + (tid >> 5)] = p;
       }
+      if ((tid & 31) == 0) { s_key[sl][tid >> 5] = key; s_sum[sl][tid >> 5] = sm; }
+      if (tid == 0) { pend_unit = unit; pend_ct = cur.ct; pend_set = sl; }
     }
-    task = ntask; b = nblk;
+    cur = nx; nx = advance(nx);
   }
+  __syncthreads();
+  if (tid == 0 && pend_unit >= 0) flush();
 }
 
 }  // namespace acq

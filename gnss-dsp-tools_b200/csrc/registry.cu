@@ -123,7 +123,7 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
 // cols: (tile columns, threads, CTAs per SM)
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
 #define PICK(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v3_smem<S, M, CW>(), 1}
-#define PICK5(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v5<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v5_smem<S, M, CW>(), TH / 32}
+#define PICK5(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v5<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v5_smem<S, M, CW>(), 1}
 #define TRY(P, S, V, CW, TH, C)                                                                                   \
   if (variant == V && schedule_matches<S>(s1))                                                                    \
     return multi ? (dump ? P(S, CW, TH, C, true, true) : P(S, CW, TH, C, true, false))                            \
