@@ -33,7 +33,7 @@ for case in CASES:
     run(*case)
 # round 2: coprime splits; copy-engine-fed pair in every tile shape (bulk copies, tensor-map copies, mbarriers,
 # named barriers), the register-loading kernels on the same plans, the fused persistent kernel, embedded lengths
-for rows, cols in ((0, 0), (1, 1), (2, 2), (3, 3), (4, 4)):
+for rows, cols in ((0, 0), (1, 1), (2, 2), (3, 3), (4, 4), (5, 0)):      # rows 0: two-role kernel, 5: block-barrier 4-row kernel
     run('163680 copy-engine-fed pair', 163680, False, 3, 5, 1, True, 1, (('v3_rows', rows), ('v3_cols', cols), ('v3_rc', 2), ('v3_g', 2)))
 run('61380 pair, 3 blocks', 30690, True, 2, 3, 3, False, 1, (('v3_cols', 3),))
 run('61380 pair, 3 blocks', 30690, True, 2, 3, 3, False, 1)
