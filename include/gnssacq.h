@@ -213,7 +213,13 @@ int gnssacq_synchronize(gnssacq_t* h);
  * bit-identical results); 0 = the 256-thread kernels.
  * "gt_split" (default 1): lengths with a coprime split N = N1*N2 (163680 = 341 x 480,
  * 61380 = 279 x 220) run the four-step in Good-Thomas form, without the twiddle pass; 0 keeps
- * the Cooley-Tukey split. Replicas must be set again afterwards. */
+ * the Cooley-Tukey split. Replicas must be set again afterwards.
+ * "v3" (default 1): those lengths run the copy-engine-fed correlate pair (bulk / tensor-map
+ * copies + mbarriers); "v3_rows" / "v3_cols" select among its instantiated tile shapes and
+ * protocols (0 = the measured best: for 480-point rows the two-role kernel, warp 0 multiply +
+ * first stage, warp 1 second stage + bulk store; the others are A/B variants, registry.cu),
+ * "v3_rc" / "v3_g" the replicas x Doppler bins of one launch pair, "lanes" the number of
+ * internal streams, "fused" (default 0) the single-launch persistent form. All bit-identical. */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Tuning: force the stage radices (forward order) of the length-N1 (which = 1) or length-N2
  * (which = 2) tile transform; ignored when their product does not match; n = 0 restores the
