@@ -485,7 +485,7 @@ __device__ __forceinline__ void cols_v3_first(float2* tile) {
 // pl.col_lag must point at the padded column table (NP + slack entries, -1 = pad column).
 // unit_hint[r*D + d]: float bits of the best eligible value any finished tile of that unit has
 // reported (zeroed by the host before the search); read at the start of a task, raised at its end.
-template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS>
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS, bool CHORE_LAST = true>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, const int* __restrict__ tile_col0,
                ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
@@ -500,6 +500,9 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
   const int tid = threadIdx.x, tc = tid & (CW - 1);
   static_assert(THREADS % 32 == 0, "whole warps");
   constexpr int NW = THREADS / 32;
+  // The per-tile chores (refilling the ring, folding the previous tile's parts) belong to the first lane of the LAST
+  // warp: the first stage has nbf * CW butterflies for THREADS threads, and it is the last warp that has a round less.
+  constexpr int kChore = CHORE_LAST ? THREADS - 32 : 0;            // 0: A/B variant
   // per-warp results of a finished tile; thread 0 folds them behind the next block barrier (two sets: the
   // warps of the next tile write the other one)
   __shared__ unsigned long long s_key[2][NW];
@@ -527,9 +530,9 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
   __syncthreads();
   float best = -1.f, sum = 0.f, hint = 0.f;
   int bestlag = 0x7fffffff, lagc = -1;
-  long long pend_unit = -1;                                    // thread 0: finished tile whose part is not written yet
+  long long pend_unit = -1;                                    // chore thread: finished tile whose part is not written yet
   int pend_ct = 0, pend_set = 0;
-  auto flush = [&]() {                                         // thread 0, behind a block barrier
+  auto flush = [&]() {                                         // chore thread, behind a block barrier
     unsigned long long key = s_key[pend_set][0];
     float sm = s_sum[pend_set][0];
 #pragma unroll
@@ -554,7 +557,7 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
       if (nur >= ck.Rc) { nur -= ck.Rc; ++nct; }
     }
     __syncthreads();                                           // every thread is done with the previous item: its slot is free
-    if (tid == 0) {
+    if (tid == kChore) {
       if (nct < ntiles) { fence_async_smem(); issue(nct, nur * ck.G + nud, nblk, (seq + 1) & 1); }
       if (pend_unit >= 0) flush();
     }
@@ -585,12 +588,12 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
         }
       }
       if ((tid & 31) == 0) { s_key[seq & 1][tid >> 5] = key; s_sum[seq & 1][tid >> 5] = sm; }
-      if (tid == 0) { pend_unit = unit; pend_ct = ct; pend_set = (int)(seq & 1); }
+      if (tid == kChore) { pend_unit = unit; pend_ct = ct; pend_set = (int)(seq & 1); }
     }
     ct = nct; ur = nur; ud = nud; b = nblk;
   }
   __syncthreads();
-  if (tid == 0 && pend_unit >= 0) flush();
+  if (tid == kChore && pend_unit >= 0) flush();
 }
 
 // =========================================================================== cols kernel, one tile slot

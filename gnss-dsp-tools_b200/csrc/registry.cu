@@ -123,18 +123,21 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
 // cols: (tile columns, threads, CTAs per SM)
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
 #define PICK(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v3_smem<S, M, CW>(), 1}
+#define PICK0(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C, false>, TH, CW, C, cols_v3_smem<S, M, CW>(), 1}
 #define PICK5(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v5<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v5_smem<S, M, CW>(), 1}
 #define TRY(P, S, V, CW, TH, C)                                                                                   \
   if (variant == V && schedule_matches<S>(s1))                                                                    \
     return multi ? (dump ? P(S, CW, TH, C, true, true) : P(S, CW, TH, C, true, false))                            \
                  : (dump ? P(S, CW, TH, C, false, true) : P(S, CW, TH, C, false, false));
   TRY(PICK, S341, 0, 8, 96, 5) TRY(PICK, S341, 1, 16, 192, 2) TRY(PICK, S341, 2, 16, 256, 2)
+  TRY(PICK0, S341, 5, 8, 96, 5)                                        // A/B: per-tile chores on thread 0 instead of the last warp
   TRY(PICK5, S341, 3, 8, 96, 6) TRY(PICK5, S341, 4, 8, 96, 7)          // one tile slot, next copy issued behind the radix-31 loads
   TRY(PICK, S279, 0, 8, 96, 5) TRY(PICK, S279, 1, 16, 160, 3)
   TRY(PICK5, S279, 3, 8, 96, 6)
 #undef TRY
 #undef PICK
 #undef PICK5
+#undef PICK0
   return ColsV3{nullptr, 0, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 10
