@@ -122,6 +122,11 @@ struct gnssacq {
   size_t xchunk_bytes = kXChunkBytes;
   cudaStream_t lane[kMaxLanes] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
+  // gnssacq_set_signal copies on its own stream, so that the capture's host-to-device transfer overlaps the replica set-up
+  // that usually follows it; whoever reads or writes the capture buffer (or synchronises for the host) joins it first
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_before_x = nullptr;
+  bool x_pending = false;
   DevBuf d_scratch_lane[kMaxLanes];
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -137,6 +142,22 @@ namespace {
 // the generic kernels implement
 bool spec_on(const gnssacq* h) { return h->use_spec && h->embed_n == 0; }
 
+// The handle's stream waits for a capture copy that is still on the copy stream (gnssacq_set_signal).
+int join_capture_copy(gnssacq* h) {
+  if (h->x_pending) {
+    CU(cudaStreamWaitEvent(h->stream, h->ev_x, 0));
+    h->x_pending = false;
+  }
+  return 0;
+}
+// Every synchronisation for the host covers that copy too (include/gnssacq.h: a pinned capture buffer is the caller's
+// again after any call that synchronises).
+#define SYNC_MAIN(h)                                             \
+  do {                                                           \
+    if (int rc_ = join_capture_copy(h)) return rc_;              \
+    CU(cudaStreamSynchronize((h)->stream));                      \
+  } while (0)
+
 int upload_nco(gnssacq* h) {
   std::vector<float2> f32(kNcoSize);
   for (int k = 0; k < kNcoSize; ++k)
@@ -145,7 +166,7 @@ int upload_nco(gnssacq* h) {
   if (int rc = h->d_nco_f64.ensure(kNcoSize * sizeof(double2))) return rc;
   CU(cudaMemcpyAsync(h->d_nco_f32.p, f32.data(), kNcoSize * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_nco_f64.p, h->nco_c128.data(), kNcoSize * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   return 0;
 }
 
@@ -224,7 +245,7 @@ int upload_plan(gnssacq* h, int N) {
     h->cube_tw.tw0 = h->d_cube0.as<float2>();
     h->cube_tw.tw1 = h->d_cube1.as<float2>();
   }
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   h->dp.N = hp.N; h->dp.N1 = hp.N1; h->dp.N2 = hp.N2;
   fill_subplan(hp.s1, h->d_tw1.as<float2>(), h->dp.s1);
   fill_subplan(hp.s2, h->d_tw2.as<float2>(), h->dp.s2);
@@ -295,6 +316,8 @@ template <class F> int with_radix_class(int rc, F&& f) {
 // wipe-off (nt = Dc*B, transform d*B+b); SRC 1: real replicas.
 template <int SRC>
 int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int B, int nt, float2* X) {
+  if (SRC == 0)
+    if (int rc = join_capture_copy(h)) return rc;              // the capture may still be on its way (gnssacq_set_signal)
   return with_radix_class(h->hp.rclass, [&](auto rc) -> int {
     constexpr int RC = decltype(rc)::value;
     const DevPlan& p = h->dp;
@@ -378,7 +401,7 @@ int v3_upload_tables(gnssacq* h, const V3Setup& v) {
   for (int t = 0; t < v.ntiles; ++t) tab[(size_t)ncol + t] = exact ? (t / per) * v.r.PB + (t % per) * v.c.CW : t * v.c.CW;
   if (int rc = h->d_v3tab.ensure(tab.size() * sizeof(int))) return rc;
   CU(cudaMemcpyAsync(h->d_v3tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));            // `tab` is a local
+  SYNC_MAIN(h);            // `tab` is a local
   std::copy(key, key + 4, h->v3tab_key);
   h->v3_ntiles = v.ntiles;
   return 0;
@@ -818,7 +841,7 @@ int gnssacq_search_sharded(gnssacq_t* h, const double* nco_freq, int32_t D, int3
     std::vector<Record> none(R);
     for (auto& r : none) { r.metric = 0.f; r.lag = 0; r.dbin = -1; r.pad = 0; }
     CU(cudaMemcpyAsync(h->d_rec.p, none.data(), none.size() * sizeof(Record), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    SYNC_MAIN(h);
   }
   if (world > 1) {
     const NcclApi* api;
@@ -833,7 +856,7 @@ int gnssacq_search_sharded(gnssacq_t* h, const double* nco_freq, int32_t D, int3
   CU(cudaGetLastError());
   std::vector<Record> rec(R);
   CU(cudaMemcpyAsync(rec.data(), h->d_merged.p, rec.size() * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   for (int r = 0; r < R; ++r) { metric[r] = rec[r].metric; lag[r] = rec[r].lag; dbin[r] = rec[r].dbin; }
   return 0;
 }
@@ -859,6 +882,9 @@ int gnssacq_create(int device, gnssacq_t** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_before_x, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(GNSSACQ_ECUDA, cudaGetErrorString(e)); }
   h->smem_optin = prop.sharedMemPerBlockOptin;
   h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
@@ -877,6 +903,7 @@ int gnssacq_create(int device, gnssacq_t** out) {
 int gnssacq_destroy(gnssacq_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  join_capture_copy(h);
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_nco_f32, &h->d_nco_f64, &h->d_x_own, &h->d_tw1, &h->d_tw2, &h->d_twm, &h->d_twm_inv, &h->d_maps, &h->d_cube0, &h->d_cube1, &h->d_C, &h->d_X,
                     &h->d_scratch, &h->d_parts, &h->d_freq, &h->d_rec, &h->d_q, &h->d_tmp, &h->d_raw, &h->d_ext,
@@ -891,6 +918,9 @@ int gnssacq_destroy(gnssacq_t* h) {
   }
   if (h->nccl_comm) { const NcclApi& api = nccl_load(nullptr); if (api.CommDestroy) api.CommDestroy(h->nccl_comm); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->ev_x) cudaEventDestroy(h->ev_x);
+  if (h->ev_before_x) cudaEventDestroy(h->ev_before_x);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -898,7 +928,7 @@ int gnssacq_destroy(gnssacq_t* h) {
 
 int gnssacq_set_stream(gnssacq_t* h, void* cuda_stream) {
   if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   return 0;
 }
@@ -914,7 +944,12 @@ int gnssacq_set_signal(gnssacq_t* h, const float* iq, int64_t n) {
   if (!h || !iq || n <= 0) return fail(GNSSACQ_EINVAL, "bad signal arguments");
   CU(cudaSetDevice(h->device));
   if (int rc = h->d_x_own.ensure((size_t)n * sizeof(float2))) return rc;
-  CU(cudaMemcpyAsync(h->d_x_own.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  // on the copy stream, behind everything queued so far (earlier searches still read the buffer)
+  CU(cudaEventRecord(h->ev_before_x, h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev_before_x, 0));
+  CU(cudaMemcpyAsync(h->d_x_own.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaEventRecord(h->ev_x, h->copy_stream));
+  h->x_pending = true;
   h->d_x = h->d_x_own.as<float2>();
   h->n_x = n;
   return 0;
@@ -1027,6 +1062,7 @@ int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, doubl
     return fail(GNSSACQ_EINVAL, "bad correlator-bank arguments");
   if (n_blocks > 65535) return fail(GNSSACQ_EINVAL, "n_blocks too large");
   if (!h->d_x) return fail(GNSSACQ_ESTATE, "gnssacq_set_signal has not been called");
+  if (int rc = join_capture_copy(h)) return rc;
   if ((int64_t)(n_blocks - 1) * block_stride + n > h->n_x)
     return fail(GNSSACQ_EINVAL, "capture too short: need (n_blocks-1)*block_stride + n = " +
                                     std::to_string((int64_t)(n_blocks - 1) * block_stride + n) + " samples, have " + std::to_string(h->n_x));
@@ -1051,7 +1087,7 @@ int gnssacq_correlate_bank(gnssacq_t* h, const int8_t* chips01, int32_t L, doubl
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_c128, h->d_bank.p, nhb * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   return 0;
 }
 
@@ -1085,13 +1121,13 @@ int gnssacq_correlate_epl(gnssacq_t* h, const float* x_c64, int32_t nx, int32_t 
   CU(cudaMemcpyAsync(d_incr, incr, hb_d, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_xsel, xsel, hb_i, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(d_csel, csel, hb_i, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));                    // hp is a local
+  SYNC_MAIN(h);                    // hp is a local
   GNSSACQ_LAUNCH(k_correlate_epl, dim3(H), dim3(kThreads), 0, h->stream, h->d_tmp.as<float2>(), n, h->d_chips.as<signed char>(), L, mode,
                  d_params, d_xsel, d_csel, d_start, d_incr, h->d_bank.as<double2>());
   h->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out_c128, h->d_bank.p, (size_t)H * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   return 0;
 }
 
@@ -1154,7 +1190,7 @@ int gnssacq_set_profiling(gnssacq_t* h, int32_t on) {
 int gnssacq_get_stage_times(gnssacq_t* h, double* ms4, int64_t* launches4, int32_t reset) {
   if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   for (auto& sp : h->spans) {
     float ms = 0.f;
 #ifndef GNSSACQ_EMU_BUILD
@@ -1202,7 +1238,7 @@ int gnssacq_search(gnssacq_t* h, const double* nco_freq, int32_t D, int32_t bloc
     else
       CU(cudaMemcpyAsync(q_dump, d_q, qn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   for (int r = 0; r < h->R; ++r) { metric[r] = rec[r].metric; lag[r] = rec[r].lag; dbin[r] = rec[r].dbin; }
   return 0;
 }
@@ -1218,7 +1254,7 @@ int gnssacq_search_grouped(gnssacq_t* h, const double* nco_freq, int32_t D, int3
   if (int rc = run_search(h, nco_freq, D, block_stride, n_blocks, normalize, n_lags, h->d_rec.as<Record>(), nullptr, group_len)) return rc;
   std::vector<Record> rec(nrec);
   CU(cudaMemcpyAsync(rec.data(), h->d_rec.p, nrec * sizeof(Record), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   for (size_t i = 0; i < nrec; ++i) { metric[i] = rec[i].metric; lag[i] = rec[i].lag; dbin[i] = rec[i].dbin; }
   return 0;
 }
@@ -1239,7 +1275,7 @@ int gnssacq_mix(gnssacq_t* h, float* iq, int64_t n, double f, double p) {
   h->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(iq, h->d_tmp.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   return 0;
 }
 
@@ -1249,6 +1285,7 @@ int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq, int64_t n, double mix_f, 
   const int edge = 3 * ntaps;                              // filtfilt default padlen = 3*max(len(a),len(b))
   if (n <= edge) return fail(GNSSACQ_EINVAL, "recording shorter than the filter padding (filtfilt would raise)");
   CU(cudaSetDevice(h->device));
+  if (int rc = join_capture_copy(h)) return rc;                // this call rewrites the capture buffer
   const long long L = n + 2ll * edge;
   const double scale = (double)kNcoSize * (double)(1ll << 50);
   const long long dp0 = (long long)floor(mix_p * scale);
@@ -1282,7 +1319,7 @@ int gnssacq_preprocess(gnssacq_t* h, const int8_t* iq, int64_t n, double mix_f, 
   h->n_x = n_out;
   if (out_c128) {
     CU(cudaMemcpyAsync(out_c128, h->d_pre128.p, (size_t)n_out * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    SYNC_MAIN(h);
   }
   return 0;
 }
@@ -1310,7 +1347,7 @@ int gnssacq_kernel_variant(gnssacq_t* h) {
 int gnssacq_synchronize(gnssacq_t* h) {
   if (!h) return fail(GNSSACQ_EINVAL, "handle is NULL");
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  SYNC_MAIN(h);
   return 0;
 }
 

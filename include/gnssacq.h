@@ -46,8 +46,11 @@ const char* gnssacq_last_error(void);
 /* Host buffers and asynchrony. Calls that take host INPUT pointers (gnssacq_set_signal,
  * gnssacq_set_replicas[_i8], gnssacq_set_replicas_from_chips, gnssacq_preprocess, the nco_freq list
  * of the search calls) enqueue their host-to-device copies on the handle's stream and may return
- * before the copy has run. Pageable memory is staged by CUDA before the call returns, so ordinary
- * malloc'd / numpy buffers may be reused at once; PINNED (page-locked) buffers are read by DMA
+ * before the copy has run (gnssacq_set_signal copies on an internal stream, behind everything the
+ * handle's stream holds at that moment, so that the transfer overlaps the replica set-up that usually
+ * follows; every call that reads or rewrites the capture, and every call that synchronises, waits
+ * for it). Pageable memory is staged by CUDA before the call returns, so ordinary malloc'd / numpy
+ * buffers may be reused at once; PINNED (page-locked) buffers are read by DMA
  * later and must stay valid and unmodified until gnssacq_synchronize() or the next call that
  * returns results to the host (gnssacq_search, gnssacq_search_grouped, gnssacq_search_sharded,
  * gnssacq_mix, gnssacq_correlate_bank), all of which synchronise the stream. */
