@@ -270,3 +270,32 @@ def test_serial_searches_match_oracle(eng):
     got = acquire_serial.search_glonass_p(x, chan, doppler, ca, ms, fs, 562500, engine=eng)
     want = orc.search_glonass_p(x, gp.p_code(), fs, 562500, chan, doppler, ca, ms)
     assert got[1] == want[1] == 612 and abs(got[0] - want[0]) <= METRIC_RTOL * want[0]
+
+
+def test_capture_copy_is_ordered_with_queued_searches(eng):
+    """gnssacq_set_signal copies on an internal stream. A search that is still queued must see the capture it was
+    given (the copy of the next capture waits for it), and the next search the new one — with pinned host buffers
+    and asynchronous searches, i.e. nothing but the library's own events orders the two streams."""
+    torch = pytest.importorskip('torch')
+    n, fs, R = 163680, 16.368e6, 4
+    chips = [random_chips(1023, 70 + i) for i in range(R)]
+    f = -orc.doppler_bins((-500, 500, 250)) / fs
+    eng.set_replicas(np.array([orc.replica(np.tile(c, 10), n, False, False) for c in chips]))
+    caps, want = [], []
+    for k in range(3):
+        x = make_x(n, 1, fs, np.tile(chips[k], 10), -250.0 + 250.0 * k, 100.25 + 37 * k, 3.0, 90 + k, False)
+        pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
+        caps.append(pin)
+        eng.set_signal(pin.numpy().view(np.complex64))
+        want.append([np.copy(a) for a in eng.search(f, n, 1, True)])          # synchronous: the expected answers
+    recs = [torch.zeros(4 * R, dtype=torch.int32, device='cuda') for _ in range(6)]
+    torch.cuda.synchronize()                                                   # the engine runs on its own non-blocking stream
+    for it in range(6):                                                        # no synchronisation in between
+        eng.set_signal(caps[it % 3].numpy().view(np.complex64))
+        eng.search_device(f, n, 1, True, 0, recs[it].data_ptr())
+    eng.synchronize()
+    for it in range(6):
+        got = recs[it].cpu().numpy().reshape(R, 4)
+        m, l, d = want[it % 3]
+        assert np.array_equal(got[:, 1], l) and np.array_equal(got[:, 2], d), it
+        assert np.array_equal(got[:, 0].view(np.float32), m), it
