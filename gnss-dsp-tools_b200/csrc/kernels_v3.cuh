@@ -357,10 +357,13 @@ __device__ __forceinline__ void cols_v3_inputs(const float2* tile, int i, int tc
 }
 
 // Outputs of that butterfly, straight into |.|, the non-coherent sum and the peak search.
-template <class S, bool MULTI, bool DUMP, int CW>
+// QREG (with MULTI): the non-coherent sums of this thread's R0 outputs live in the register array qacc[R0] across
+// the blocks of a task instead of in shared memory (one FADD per output and block instead of LDS + FADD + STS);
+// the slot of an output is fixed at compile time: 0 for output 0, then in the order the outputs are produced.
+template <class S, bool MULTI, bool DUMP, int CW, bool QREG = false>
 __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a, const float2* bq, const float2 s0, int i, float* qs, int tc,
                                                const DevPlan& pl, int lagc, int b, bool last, int n_lags, float scale, float* qd, float hint,
-                                               float& best, int& bestlag, float& sum) {
+                                               float& best, int& bestlag, float& sum, float* qacc = nullptr) {
   constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
   const int N2 = pl.N2, Nfull = pl.N;
   auto lag_of = [&](int n1i, int q) -> int {
@@ -375,13 +378,20 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
   if constexpr (S::kPfa) n1i = __ldg(&pl.n1_of_pos[i]);
   float floor_ = fmaxf(fmaxf(best, hint), 0.f);
   // outputs v[t] with digits Q...: magnitudes, accumulation over blocks, sum, peak candidates
-  auto sink = [&](auto digits, const float2* v) {
+  auto sink = [&](auto digits, auto slot0, const float2* v) {
     constexpr auto dg = seq_array(decltype(digits){});
-    constexpr int NB = (int)dg.n;
+    constexpr int NB = (int)dg.n, q0 = decltype(slot0)::value;
     float acc[NB];
 #pragma unroll
     for (int t = 0; t < NB; ++t) acc[t] = sqrt_fast(fmaf(v[t].x, v[t].x, v[t].y * v[t].y));
-    if constexpr (MULTI) {
+    if constexpr (MULTI && QREG) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        if (b > 0) acc[t] += qacc[q0 + t];
+        qacc[q0 + t] = acc[t];
+      }
+      if (!last) return;
+    } else if constexpr (MULTI) {
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         float* q1 = qp + dg.v[t] * m0 * CW;
@@ -423,7 +433,7 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
   };
   if constexpr (kRader31On && R0 == 31) {
     // two 15-point convolutions (fft_core.cuh); block 2 arrives negated, |.| does not see it
-    rader31_outputs(x0, a, bq, [&](const float2 dc) { sink(std::integer_sequence<int, 0>{}, &dc); },
+    rader31_outputs(x0, a, bq, [&](const float2 dc) { sink(std::integer_sequence<int, 0>{}, std::integral_constant<int, 0>{}, &dc); },
                     [&](auto N3, const float2* re, const float2* im) {
                       float2 v[10];
 #pragma unroll
@@ -431,10 +441,11 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
                         v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);
                         v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);
                       }
-                      sink(r31_block_digits<decltype(N3)::value>(std::make_integer_sequence<int, 10>{}), v);
+                      sink(r31_block_digits<decltype(N3)::value>(std::make_integer_sequence<int, 10>{}),
+                           std::integral_constant<int, 1 + 10 * decltype(N3)::value>{}, v);
                     });
   } else {
-    sink(std::integer_sequence<int, 0>{}, &s0);
+    sink(std::integer_sequence<int, 0>{}, std::integral_constant<int, 0>{}, &s0);
     prime_outputs_batched<R0, 1, H>(x0, a, bq, [&](auto K0c, auto NKc, const float2* re, const float2* im) {
       constexpr int k0 = decltype(K0c)::value, nk = decltype(NKc)::value;
       float2 v[2 * nk];
@@ -443,23 +454,24 @@ __device__ __forceinline__ void cols_v3_outputs(const float2 x0, const float2* a
         v[2 * t] = make_float2(re[t].x - im[t].y, re[t].y + im[t].x);          // inverse output k      = re + i*im
         v[2 * t + 1] = make_float2(re[t].x + im[t].y, re[t].y - im[t].x);      // inverse output R0 - k = re - i*im
       }
-      sink(prime_pair_digits<R0, k0>(std::make_integer_sequence<int, 2 * nk>{}), v);
+      sink(prime_pair_digits<R0, k0>(std::make_integer_sequence<int, 2 * nk>{}), std::integral_constant<int, 2 * k0 - 1>{}, v);
     });
   }
 }
 
-template <class S, bool MULTI, bool DUMP, int CW, int THREADS>
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS, bool QREG = false>
 __device__ __forceinline__ void cols_v3_last(const float2* tile, float* qs, const DevPlan& pl, int lagc, int b, bool last,
                                             int n_lags, float scale, float* qd, float hint,
-                                            float& best, int& bestlag, float& sum) {
+                                            float& best, int& bestlag, float& sum, float* qacc = nullptr) {
   constexpr int R0 = S::radix(0), m0 = S::stride(0), H = (R0 - 1) / 2;
   static_assert(R0 % 2 == 1 && R0 >= 7, "prime radix fused with the epilogue");
   const int tc = threadIdx.x & (CW - 1), tb = threadIdx.x / CW;
   constexpr int nb = THREADS / CW;
+  static_assert(!QREG || nb >= m0, "register accumulators: one butterfly per thread");
   for (int i = tb; i < m0; i += nb) {
     float2 a[H + 1], bq[H + 1], x0, s0;
     cols_v3_inputs<S, CW>(tile, i, tc, x0, a, bq, s0);
-    cols_v3_outputs<S, MULTI, DUMP, CW>(x0, a, bq, s0, i, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
+    cols_v3_outputs<S, MULTI, DUMP, CW, QREG>(x0, a, bq, s0, i, qs, tc, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum, qacc);
   }
 }
 
@@ -485,7 +497,7 @@ __device__ __forceinline__ void cols_v3_first(float2* tile) {
 // pl.col_lag must point at the padded column table (NP + slack entries, -1 = pad column).
 // unit_hint[r*D + d]: float bits of the best eligible value any finished tile of that unit has
 // reported (zeroed by the host before the search); read at the start of a task, raised at its end.
-template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS, bool CHORE_LAST = true>
+template <class S, bool MULTI, bool DUMP, int CW, int THREADS, int MINCTAS, bool CHORE_LAST = true, bool QREG = false>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, const int* __restrict__ tile_col0,
                ChunkV3 ck, int B, int D, int d0, int n_lags, float scale, int ntiles,
@@ -494,8 +506,9 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
   static_assert(S::NS == 2, "two-stage columns schedule");
   static_assert(CW == 8 || CW == 16, "tile width");
   constexpr int N1 = S::F, TILE = N1 * CW, SLOT = cols_v3_slot<S, CW>();
-  float* qs = reinterpret_cast<float*>(smem + 2 * SLOT);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v3_smem<S, MULTI, CW>() - 16);
+  float* qs = reinterpret_cast<float*>(smem + 2 * SLOT);          // unused with QREG (the launch then passes the size without it)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + cols_v3_smem<S, MULTI && !QREG, CW>() - 16);
+  float qacc[QREG ? S::radix(0) : 1];
   const int N = pl.N;
   const int tid = threadIdx.x, tc = tid & (CW - 1);
   static_assert(THREADS % 32 == 0, "whole warps");
@@ -573,7 +586,7 @@ k_corr_cols_v3(DevPlan pl, const GNSSACQ_GRID_CONSTANT TensorMap map, int zmul, 
     mbar_wait(&full[seq & 1], (seq >> 1) & 1u);
     cols_v3_first<S, CW, THREADS>(tile);
     __syncthreads();
-    if (lagc >= 0) cols_v3_last<S, MULTI, DUMP, CW, THREADS>(tile, qs, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum);
+    if (lagc >= 0) cols_v3_last<S, MULTI, DUMP, CW, THREADS, QREG>(tile, qs, pl, lagc, b, last, n_lags, scale, qd, hint, best, bestlag, sum, qacc);
     if (last) {
       // per warp: the sum always, the key only if some lane holds a candidate (rare once the floor is warm)
       unsigned long long key = bestlag != 0x7fffffff ? pack_key(best, bestlag) : 0ull;

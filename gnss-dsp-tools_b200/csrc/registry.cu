@@ -124,12 +124,20 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
 #define PICK(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v3_smem<S, M, CW>(), 1}
 #define PICK0(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C, false>, TH, CW, C, cols_v3_smem<S, M, CW>(), 1}
+// multi-block searches with the non-coherent sums in registers (no q array in shared memory); single-block calls get the plain kernel
+#define PICKQ(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v3<S, M, DUMP, CW, TH, C, true, M>, TH, CW, C, cols_v3_smem<S, false, CW>(), 1}
 #define PICK5(S, CW, TH, C, M, DUMP) ColsV3{k_corr_cols_v5<S, M, DUMP, CW, TH, C>, TH, CW, C, cols_v5_smem<S, M, CW>(), 1}
 #define TRY(P, S, V, CW, TH, C)                                                                                   \
   if (variant == V && schedule_matches<S>(s1))                                                                    \
     return multi ? (dump ? P(S, CW, TH, C, true, true) : P(S, CW, TH, C, true, false))                            \
                  : (dump ? P(S, CW, TH, C, false, true) : P(S, CW, TH, C, false, false));
+  // default: 8-column tiles x 96 threads x 5 CTAs per SM; multi-block searches keep their non-coherent sums in registers
+  // (4 CTAs per SM, no q array in shared memory: +1-2 % on 61380 x 20 blocks and 30690 x 20, r04)
+  if (variant == 0 && multi && schedule_matches<S341>(s1)) return dump ? PICKQ(S341, 8, 96, 4, true, true) : PICKQ(S341, 8, 96, 4, true, false);
+  if (variant == 0 && multi && schedule_matches<S279>(s1)) return dump ? PICKQ(S279, 8, 96, 4, true, true) : PICKQ(S279, 8, 96, 4, true, false);
   TRY(PICK, S341, 0, 8, 96, 5) TRY(PICK, S341, 1, 16, 192, 2) TRY(PICK, S341, 2, 16, 256, 2)
+  TRY(PICK, S341, 6, 8, 96, 5) TRY(PICK, S279, 6, 8, 96, 5)            // A/B: non-coherent sums in shared memory
+  TRY(PICKQ, S279, 7, 8, 96, 5)
   TRY(PICK0, S341, 5, 8, 96, 5)                                        // A/B: per-tile chores on thread 0 instead of the last warp
   TRY(PICK5, S341, 3, 8, 96, 6) TRY(PICK5, S341, 4, 8, 96, 7)          // one tile slot, next copy issued behind the radix-31 loads
   TRY(PICK, S279, 0, 8, 96, 5) TRY(PICK, S279, 1, 16, 160, 3)
@@ -138,6 +146,7 @@ ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant) {
 #undef PICK
 #undef PICK5
 #undef PICK0
+#undef PICKQ
   return ColsV3{nullptr, 0, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 10

@@ -242,7 +242,7 @@ def test_fused_kernel_group_shapes_163680(eng, rc, g, sets, tpt):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2), (0, 3, 3)])   # 279 x 220: tile shapes; 3 = single-slot columns kernel
+@pytest.mark.parametrize('rows,cols,blocks', [(0, 0, 3), (1, 1, 2), (0, 3, 3), (0, 6, 3), (1, 7, 2)])   # 279 x 220: tile shapes; 3 = single-slot columns kernel; 6, 7 = non-coherent sums in registers
 def test_v3_non_coherent_blocks_61380(eng, rows, cols, blocks):
     """279 x 220 with several non-coherent blocks: the (Doppler, block) list walked by the rows
     kernel (split over grid.z), q accumulated in shared memory by the columns kernel."""
