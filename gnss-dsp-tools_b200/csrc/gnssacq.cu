@@ -99,6 +99,7 @@ struct gnssacq {
   bool use_v3 = true;
   int v3_rows_variant = 0, v3_cols_variant = 0;      // tile shapes (registry.cu), A/B
   int v3_rc = 0, v3_g = 0;                           // replicas x Doppler bins per launch (0 = automatic)
+  bool fwd_v6 = true;                                // forward rows pass through k_fwd_rows_v6 where instantiated
   DevBuf d_v3tab;                                    // padded column table + tile origins
   // one persistent kernel per Doppler chunk (kernels_fused.cuh) instead of the pair: correct, measured 14 %
   // slower than the pair on config 2 (profiles/README.md r03f), hence off unless asked for
@@ -343,7 +344,17 @@ int forward(gnssacq* h, const float* rep, const double* d_freq, int stride, int 
       if (int rc2 = allow_smem(h, kr, smr)) return rc2;
       GNSSACQ_LAUNCH(kc, dim3((p.N2 + kTileW - 1) / kTileW, nt), dim3(kThreads), smc, h->stream,
                      p, h->d_x, rep, d_freq, tab, stride, B, X);
-      GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, nt), dim3(kThreads), smr, h->stream, p, X);
+      // rows pass: the copy-engine-fed two-role kernel for coprime plans that have one ("fwd_v6", default on)
+      const FwdRowsV6 f6 = (spec_on(h) && h->use_v3 && h->fwd_v6 && p.gt) ? find_fwd_rows_v6(p.s2) : FwdRowsV6{nullptr, 0, 0, 0, 0};
+      if (f6.fn && f6.smem <= h->smem_optin) {
+        if (int rc2 = allow_smem(h, f6.fn, f6.smem)) return rc2;
+        const int nrt = (p.N1 + f6.T - 1) / f6.T;
+        // one wave of CTAs (equal work each); a CTA walks its share of the transforms with the rows of its tile
+        const int split = std::max(1, std::min(nt, h->num_sms * f6.ctas_per_sm / nrt));
+        GNSSACQ_LAUNCH(f6.fn, dim3(nrt, split), dim3(f6.threads), f6.smem, h->stream, p, X, nt);
+      } else {
+        GNSSACQ_LAUNCH(kr, dim3((p.N1 + kTileW - 1) / kTileW, nt), dim3(kThreads), smr, h->stream, p, X);
+      }
       h->launches += 2;
     }
     CU(cudaGetLastError());
@@ -1152,6 +1163,7 @@ int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value) {
   if (std::string(name) == "fused_tpt") { h->fused_tpt = value; return 0; }
   if (std::string(name) == "v3_rows") { h->v3_rows_variant = value; return 0; }
   if (std::string(name) == "v3_cols") { h->v3_cols_variant = value; return 0; }
+  if (std::string(name) == "fwd_v6") { h->fwd_v6 = value != 0; return 0; }
   if (std::string(name) == "v3_rc") { h->v3_rc = value; return 0; }
   if (std::string(name) == "v3_g") { h->v3_g = value; return 0; }
   if (std::string(name) == "overlap_chunks") { h->overlap = value != 0; return 0; }

@@ -319,6 +319,107 @@ k_corr_rows_v6(DevPlan pl, const float2* __restrict__ X, const float2* __restric
   }
 }
 
+// =========================================================================== forward rows kernel, two roles
+// The length-N2 row transforms of the forward pass (capture spectra X[d][b] and replica spectra C[r]) in the
+// structure of k_corr_rows_v6: the rows of a 2-row tile arrive by one bulk copy per transform, warp 0 runs the
+// forward radix-RA butterflies over the stride-RB digit (the Good-Thomas input permutation fpos2 is applied as it
+// reads: its RA source offsets are per-lane constants), warp 1 the radix-RB butterflies, and every stage-B lane
+// writes its finished group of RB contiguous outputs back in place with its own 256-byte bulk store. Replaces the
+// register-loading k_fwd_rows_s (48 % long-scoreboard stalls, profiles/r04_fwd_ncu_summary.txt) for 480 = 15 x 32.
+// grid = (row tiles, splits of the transform list); X: [nt][N] in place.
+template <class S> __host__ __device__ constexpr size_t fwd_rows_v6_smem() { return rows_v6_smem<S>(); }
+template <class S, int MINCTAS>
+__global__ void __launch_bounds__(64, MINCTAS)
+k_fwd_rows_v6(DevPlan pl, float2* __restrict__ X, int nt) {
+  GNSSACQ_DYN_SMEM(float2, smem);
+  static_assert(S::NS == 2 && S::kPfa, "two coprime stages");
+  constexpr int T = 2;
+  constexpr int N2 = S::F, RA = S::radix(0), RB = S::radix(1), PB = v3_pitch(RB), NP = RA * PB;
+  static_assert(RB == 32 && T * RA <= 32, "one lane per stage-A column, stage B within one warp");
+  constexpr int XT = T * N2, ET = T * NP;
+  float2* xbuf = smem;
+  float2* ebuf = smem + 2 * XT;
+  unsigned long long* xfull = reinterpret_cast<unsigned long long*>(ebuf + 2 * ET);
+  unsigned long long* efull = xfull + 2;
+  unsigned long long* efree = xfull + 4;
+  int* src_of_pos = reinterpret_cast<int*>(ebuf);               // inverse of fpos2 (tile position -> sample index within the row), built in the
+                                                                // first exchange buffer and read into registers before that buffer is used
+  const int N = pl.N, N1 = pl.N1;
+  const int row0 = blockIdx.x * T;
+  const int nrows = imin(T, N1 - row0);
+  const int per = (nt + gridDim.y - 1) / gridDim.y;
+  const int it0 = blockIdx.y * per, nit = imin(per, nt - it0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned xbytes = (unsigned)nrows * N2 * sizeof(float2);
+
+  auto rows_of = [&](int it) -> float2* { return X + (long long)(it0 + it) * N + (long long)row0 * N2; };
+  auto issue = [&](int it) {                                   // rows of transform it0 + it -> ring slot it & 1
+    mbar_arrive_expect(&xfull[it & 1], xbytes);
+    bulk_g2s(xbuf + (it & 1) * XT, rows_of(it), xbytes, &xfull[it & 1]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&xfull[s], 1); mbar_init(&efull[s], 32); mbar_init(&efree[s], 1); }
+    mbar_fence_init();
+    for (int it = 0; it < 2 && it < nit; ++it) issue(it);
+  }
+  for (int e = tid; e < N2; e += 64) src_of_pos[__ldg(&pl.fpos2[e])] = e;
+  __syncthreads();                                             // barriers and the inverse map visible to both warps
+
+  if (warp == 0) {
+    int src[RA];                                               // stage A of column b = lane reads tile positions a * RB + b
+#pragma unroll
+    for (int a = 0; a < RA; ++a) src[a] = src_of_pos[a * RB + lane];
+    __syncwarp();                                              // every lane holds its offsets before the first stage-A store reuses the buffer
+    for (int it = 0; it < nit; ++it) {
+      const int e = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      float2* et = ebuf + e * ET;
+      mbar_wait(&xfull[e], ph);
+      if (it >= 2) mbar_wait(&efree[e], ph ^ 1u);              // the stores of transform it-2 have drained this buffer
+      for (int ra = 0; ra < nrows; ++ra) {
+        const float2* xp = xbuf + e * XT + ra * N2;
+        float2 y[RA];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) y[a] = xp[src[a]];
+        Dft<RA>::run(y);
+        float2* ep = et + ra * NP + lane;
+#pragma unroll
+        for (int a = 0; a < RA; ++a) ep[a * PB] = y[a];
+      }
+      __syncwarp();                                            // every lane is done with ring slot e
+      if (lane == 0 && it + 2 < nit) { fence_async_smem(); issue(it + 2); }
+      mbar_arrive(&efull[e]);
+    }
+  } else {
+    const bool act_b = lane < nrows * RA;                      // stage-B butterfly: group lane = row * RA + a'
+    const int brow = lane / RA, ba = lane - brow * RA;
+    for (int it = 0; it < nit; ++it) {
+      const int e = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      float2* et = ebuf + e * ET;
+      mbar_wait(&efull[e], ph);
+      if (it >= 1) {
+        if (act_b) bulk_wait_read<0>();                        // my store of transform it-1 has read its group
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&efree[e ^ 1]);
+      }
+      if (act_b) {
+        float4* p4 = reinterpret_cast<float4*>(et + lane * PB);
+        float2 v[RB];
+#pragma unroll
+        for (int q = 0; q < RB / 2; ++q) { const float4 t = p4[q]; v[2 * q] = make_float2(t.x, t.y); v[2 * q + 1] = make_float2(t.z, t.w); }
+        Dft<RB>::run(v);
+#pragma unroll
+        for (int q = 0; q < RB / 2; ++q) p4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+        fence_async_smem();                                    // these writes are read by my bulk store
+        bulk_s2g(rows_of(it) + brow * N2 + ba * RB, et + lane * PB, (unsigned)(RB * sizeof(float2)));
+        bulk_commit();
+      }
+    }
+    if (act_b) bulk_wait_all<0>();                             // shared memory must outlive the last stores
+  }
+}
+
 // =========================================================================== cols kernel
 // ring slots start on 128-byte boundaries (tensor-map copies need it)
 template <class S, int CW> __host__ __device__ constexpr int cols_v3_slot() { return (S::F * CW + 15) / 16 * 16; }   // float2 per slot

@@ -113,11 +113,16 @@ RowsV3 find_rows_v3(const SubPlan& s2, int variant) {
   // balanced kernel (the two halves of the CTA alternate on stage B): 4 warps, stage B = 2 warps
   if (variant == 4 && schedule_matches<S480>(s2))
     return RowsV3{k_corr_rows_v4<S480, 4, 128, 3>, 128, 4, 3, rows_v4_smem<S480, 4>(), S480::radix(0), S480::radix(1), v3_pitch(S480::radix(1))};
+  // (forward counterpart below)
   // default for 480: two roles, warp 0 = stage A of a 2-row tile, warp 1 = stage B + bulk store, no block barrier
   // (r04d: correlate stage 1.63 -> 1.59 ms per config-2 step against the 4-row x 128-thread kernel, now variant 5)
   if (variant == 0 && schedule_matches<S480>(s2))
     return RowsV3{k_corr_rows_v6<S480, 7>, 64, 2, 7, rows_v6_smem<S480>(), S480::radix(0), S480::radix(1), v3_pitch(S480::radix(1))};
   return RowsV3{nullptr, 0, 0, 0, 0, 0, 0, 0};
+}
+FwdRowsV6 find_fwd_rows_v6(const SubPlan& s2) {
+  if (schedule_matches<S480>(s2)) return FwdRowsV6{k_fwd_rows_v6<S480, 7>, 64, 2, 7, fwd_rows_v6_smem<S480>()};
+  return FwdRowsV6{nullptr, 0, 0, 0, 0};
 }
 #elif GNSSACQ_REG_PART == 9
 // cols: (tile columns, threads, CTAs per SM)

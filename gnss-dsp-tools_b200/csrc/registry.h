@@ -36,6 +36,10 @@ struct RowsV3 { rows_v3_fn fn; int threads, T, ctas_per_sm; size_t smem; int RA,
 struct ColsV3 { cols_v3_fn fn; int threads, CW, ctas_per_sm; size_t smem; int parts_per_tile; };   // parts per (unit, tile): 1, or one per warp
 RowsV3 find_rows_v3(const SubPlan& s2, int variant);
 ColsV3 find_cols_v3(const SubPlan& s1, bool multi, bool dump, int variant);   // dump: also writes the q grid (tests)
+// forward rows kernel in the two-role structure (k_fwd_rows_v6): grid (row tiles of T rows, splits of the transform list)
+typedef void (*fwd_rows_v6_fn)(DevPlan, float2*, int);
+struct FwdRowsV6 { fwd_rows_v6_fn fn; int threads, T, ctas_per_sm; size_t smem; };
+FwdRowsV6 find_fwd_rows_v6(const SubPlan& s2);
 
 // Fused persistent correlate kernel (kernels_fused.cuh): both task types in one launch per Doppler chunk.
 typedef void (*fused_fn)(DevPlan, const TensorMap, const int*, FusedJob, FusedSync, const float2*, const float2*, float2*, Part*, float*, unsigned*);
