@@ -222,7 +222,8 @@ int gnssacq_synchronize(gnssacq_t* h);
  * protocols (0 = the measured best: for 480-point rows the two-role kernel, warp 0 multiply +
  * first stage, warp 1 second stage + bulk store; the others are A/B variants, registry.cu),
  * "v3_rc" / "v3_g" the replicas x Doppler bins of one launch pair, "lanes" the number of
- * internal streams, "fused" (default 0) the single-launch persistent form. All bit-identical. */
+ * internal streams, "fused" (default 0) the single-launch persistent form, "fwd_v6" (default 1) the
+ * copy-engine-fed rows pass of the forward transforms where one is instantiated. All bit-identical. */
 int gnssacq_set_option(gnssacq_t* h, const char* name, int32_t value);
 /* Tuning: force the stage radices (forward order) of the length-N1 (which = 1) or length-N2
  * (which = 2) tile transform; ignored when their product does not match; n = 0 restores the
