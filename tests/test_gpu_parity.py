@@ -208,6 +208,33 @@ def test_full_size_config2_property(eng):
     assert np.array_equal(np.where(take1, d1 + 40, d0), df)
 
 
+def _oracle_cfg2_task(t):
+    import gnsstools.gps.ca as ca
+    x, prn, grid = t
+    return orc.search(x, ca.ca_code(prn), 16368000.0, 163680, grid, 1, normalize=True, mod_L=True, lag_limit=16368, periods=10)
+
+
+def test_full_size_config2_every_prn_against_the_oracle(eng):
+    """BASELINE config 2 in full — all 32 PRNs x 81 Doppler bins x 163680 lags of one capture — against the oracle
+    (fanned out over the host cores like acquire-gps-l1.py:105-108): code phase and Doppler bin exact for every PRN,
+    planted or noise-only, metric within the north-star tolerance."""
+    import multiprocessing as mp
+    import os
+    from gnsstools import acquire, synth
+    sig = acquire.Signal('gps.ca', 16368000.0, 163680, lambda ms: ms // 10, normalize=True, mod_L=True, periods=10)
+    planted = [(3, -7250.0, 100.0, 1.5), (11, 2500.0, 511.5, 1.5), (22, 9750.0, 1000.25, 1.5), (30, -250.0, 3.0, 1.5)]
+    x = synth.capture(sig, ms=10, sats=planted, seed=5, extra_ms=0)
+    grid = (-10000.0, 10000.0, 250.0)
+    prns = list(range(1, 33))
+    got = acquire.acquire(sig, x, prns, grid, 10, engine=eng, lag_limit=16368)
+    x64 = x.astype(np.complex128)
+    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 16)) as pool:
+        want = pool.map(_oracle_cfg2_task, [(x64, p, grid) for p in prns])
+    for prn, g, w in zip(prns, got, want):
+        assert g[1] == w[1] and g[2] == w[2], (prn, g, w)             # code phase (chips) and Doppler (Hz): exact
+        assert abs(g[0] - w[0]) <= METRIC_RTOL * w[0], (prn, g, w)
+
+
 # --------------------------------------------------------------------------- replica builder / correlator bank
 @pytest.mark.parametrize('signal,keys', [('gps-l1', [1, 17, 32]), ('gps-l1cd', [4]), ('galileo-e1b', [11, 12]),
                                          ('gps-l5i', [2]), ('glonass-l1', [None]), ('beidou-b2ap', [9])])
