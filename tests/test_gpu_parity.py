@@ -235,6 +235,36 @@ def test_full_size_config2_every_prn_against_the_oracle(eng):
         assert abs(g[0] - w[0]) <= METRIC_RTOL * w[0], (prn, g, w)
 
 
+def _oracle_cfg4_task(t):
+    x, chips, fs, n, grid, blocks = t
+    ref, (idx, dbin, _) = orc.search(x, chips, fs, n, grid, blocks, pad=True, return_grid=True)
+    return ref, (idx, dbin)
+
+
+def test_config4_shape_many_replicas_against_the_oracle(eng):
+    """The shape of BASELINE config 4 (reference-style: L5 codes, n = 30690 zero-padded to 61380, 20 non-coherent
+    blocks) with 16 replicas x 25 Doppler bins against the oracle — the multi-block columns kernel with its
+    non-coherent sums in registers, at the launch shapes the real job uses."""
+    import multiprocessing as mp
+    import os
+    n, fs, blocks, R = 30690, 30.69e6, 20, 16
+    grid = (-3000.0, 3000.0, 250.0)
+    chips = [random_chips(10230, 300 + i) for i in range(R)]
+    x = make_x(n, blocks, fs, chips[5], grid[0] + 7 * grid[2], 1234.5, 2.0, 17, True)
+    x += make_x(n, blocks, fs, chips[11], grid[0] + 20 * grid[2], 77.25, 2.0, 18, True) - make_x(n, blocks, fs, chips[11], 0.0, 0.0, 0.0, 18, True)
+    x64 = x.astype(np.complex128)
+    eng.set_signal(x)
+    eng.set_replicas(np.array([orc.replica(c, n, True, False) for c in chips]))
+    f = -orc.doppler_bins(grid) / fs
+    m, l, d = eng.search(f, n, blocks, False)
+    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 16)) as pool:
+        want = pool.map(_oracle_cfg4_task, [(x64, c, fs, n, grid, blocks) for c in chips])
+    for i, (ref, (idx, dbin)) in enumerate(want):
+        assert (int(l[i]), int(d[i])) == (idx, dbin), i
+        assert abs(m[i] - ref[0]) <= METRIC_RTOL * ref[0], (i, m[i], ref[0])
+    assert int(d[5]) == 7 and int(d[11]) == 20
+
+
 # --------------------------------------------------------------------------- replica builder / correlator bank
 @pytest.mark.parametrize('signal,keys', [('gps-l1', [1, 17, 32]), ('gps-l1cd', [4]), ('galileo-e1b', [11, 12]),
                                          ('gps-l5i', [2]), ('glonass-l1', [None]), ('beidou-b2ap', [9])])
