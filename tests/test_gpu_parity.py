@@ -265,6 +265,35 @@ def test_config4_shape_many_replicas_against_the_oracle(eng):
     assert int(d[5]) == 7 and int(d[11]) == 20
 
 
+def _oracle_cfg3_task(t):
+    x, chips, fs, n, grid = t
+    ref, (idx, dbin, _) = orc.search(x, chips, fs, n, grid, 1, pad=True, boc=True, return_grid=True)
+    return ref, (idx, dbin)
+
+
+def test_config3_native_shape_many_replicas_against_the_oracle(eng):
+    """The shape of BASELINE config 3 at its native rate (Galileo E1: 4092 chips, BOC(1,1), 4 ms at 20.46 Msps,
+    zero-padded to 2n = 163680) with 12 replicas x 41 Doppler bins against the oracle: launches of 12 x 8 units
+    through the forward rows kernel, the two-role rows kernel and the columns kernel."""
+    import multiprocessing as mp
+    import os
+    n, fs, R = 81840, 20.46e6, 12
+    grid = (-1000.0, 1000.0, 50.0)
+    chips = [random_chips(4092, 500 + i) for i in range(R)]
+    x = make_x(n, 1, fs, chips[3], grid[0] + 9 * grid[2], 1500.5, 3.0, 21, True, True)
+    x64 = x.astype(np.complex128)
+    eng.set_signal(x)
+    eng.set_replicas(np.array([orc.replica(c, n, True, True) for c in chips]))
+    f = -orc.doppler_bins(grid) / fs
+    m, l, d = eng.search(f, n, 1, False)
+    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 12)) as pool:
+        want = pool.map(_oracle_cfg3_task, [(x64, c, fs, n, grid) for c in chips])
+    for i, (ref, (idx, dbin)) in enumerate(want):
+        assert (int(l[i]), int(d[i])) == (idx, dbin), i
+        assert abs(m[i] - ref[0]) <= METRIC_RTOL * ref[0], (i, m[i], ref[0])
+    assert int(d[3]) == 9
+
+
 # --------------------------------------------------------------------------- replica builder / correlator bank
 @pytest.mark.parametrize('signal,keys', [('gps-l1', [1, 17, 32]), ('gps-l1cd', [4]), ('galileo-e1b', [11, 12]),
                                          ('gps-l5i', [2]), ('glonass-l1', [None]), ('beidou-b2ap', [9])])
