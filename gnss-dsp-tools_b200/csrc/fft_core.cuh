@@ -526,6 +526,39 @@ __device__ __forceinline__ void rader31_outputs(const float2 x0, const float2* a
                  [&](auto N3, const float2* y) { batch(N3, yc[decltype(N3)::value], y); });
 }
 
+// The whole forward 31-point transform of one thread's registers through the two convolutions (outputs in natural
+// order, block 2's negation undone by negated additions).
+struct Dft31Rader {
+  static __device__ __forceinline__ void run(float2* v) {
+    float2 a[16], bs[16];
+    const float2 x0 = v[0];
+    static_for<1, 16>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const float2 u = v[j], w = v[31 - j];
+      a[j] = cadd(u, w);
+      bs[j] = r31_flip_b(j) ? csub(w, u) : csub(u, w);
+    });
+    rader31_outputs(x0, a, bs, [&](const float2 dc) { v[0] = dc; },
+                    [&](auto N3, const float2* re, const float2* im) {
+                      constexpr int n3 = decltype(N3)::value;
+                      static_for<0, 5>([&](auto Pp) {
+                        constexpr int p = decltype(Pp)::value, n = r31_crt(n3, p), k = r31_rep(n);
+                        constexpr bool pos = r31_sign(n) > 0;
+                        float2 u, w;                             // re - i*im', re + i*im' (forward sign), im' as delivered
+                        if constexpr (n3 == 2) {
+                          u = make_float2(-re[p].x - im[p].y, im[p].x - re[p].y);
+                          w = make_float2(im[p].y - re[p].x, -re[p].y - im[p].x);
+                        } else {
+                          u = make_float2(re[p].x + im[p].y, re[p].y - im[p].x);
+                          w = make_float2(re[p].x - im[p].y, re[p].y + im[p].x);
+                        }
+                        v[pos ? k : 31 - k] = u;
+                        v[pos ? 31 - k : k] = w;
+                      });
+                    });
+  }
+};
+
 // NOTW: prime-factor transform, no stage twiddles.
 template <int P, bool INV, int ES = 0, int CS = 1, bool NOTW = false>
 __device__ __forceinline__ void stage_tile_split(float2* tile, int ncols, int F, int m,

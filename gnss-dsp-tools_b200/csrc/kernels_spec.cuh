@@ -45,6 +45,11 @@ struct Sub {
 };
 
 constexpr bool is_split_radix(int R) { return R == 31; }
+#ifdef GNSSACQ_NO_FWD_RADER31
+constexpr bool kFwdRader31 = false;      // A/B builds: the forward radix-31 stage shared by a warp pair
+#else
+constexpr bool kFwdRader31 = true;
+#endif
 // butterflies a thread keeps in flight per loop trip: small radices need several for ILP
 constexpr int stage_unroll(int R) { return R <= 5 ? 4 : (R <= 10 ? 2 : 1); }
 // butterflies whose global loads the columns kernel's first stage keeps in flight per thread
@@ -464,7 +469,22 @@ template <class S, int J, int ES, int CS>
 __device__ __forceinline__ void fwd_stage_smem(float2* tile, int ncols, const float2* __restrict__ twbase, int twoff) {
   constexpr int R = S::radix(J), m = S::stride(J), nbf = S::F / R;
   const int tc = threadIdx.x & (kTW - 1);
-  if constexpr (is_split_radix(R)) {
+  if constexpr (R == 31 && S::kPfa && kRader31On && kFwdRader31) {
+    // one thread per butterfly, radix 31 as two 15-point convolutions (fft_core.cuh); a butterfly's 31 elements are its own
+    const int tb = threadIdx.x / kTW;
+    constexpr int nb = kThreads / kTW;
+    if (tc < ncols)
+      for (int bf = tb; bf < nbf; bf += nb) {
+        const int blk = bf / m, i = bf - blk * m;
+        float2* p = tile + (blk * R * m + i) * ES + tc * CS;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = p[q * m * ES];
+        Dft31Rader::run(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) p[q * m * ES] = v[q];
+      }
+  } else if constexpr (is_split_radix(R)) {
     stage_tile_split<R, false, ES, CS, S::kPfa>(tile, ncols, S::F, m, twbase);
   } else {
     const int tb = threadIdx.x / kTW;
